@@ -1,0 +1,6 @@
+"""gadfly_b200: B200-native (sm_100a) GP hot path behind gadfly's Python API."""
+__version__ = "0.1.0"
+
+from . import units  # noqa: F401
+from .core import *  # noqa: F401,F403
+from .terms import *  # noqa: F401,F403

@@ -1,0 +1,136 @@
+/*
+ * gadfly_b200 -- C ABI of the B200 (sm_100a) GP hot path.
+ *
+ * This is the drop-in boundary: the entry points below are what the reference's
+ * binding to its native solver would bind for this path.  In the reference the
+ * native solver is celerite2's pybind11 module ``celerite2.driver`` reached through
+ * ``celerite2.GaussianProcess`` / ``celerite2.terms``; each entry point names the
+ * reference call site (file:line under the reference repo) it stands in for.
+ *
+ * Conventions
+ *  - All floating-point data is IEEE binary64.  Time is in 1/uHz (1e6 s), angular
+ *    frequency in rad*uHz, flux in ppm (reference gadfly/gp.py:61-126).
+ *  - A "sequence" is one light curve + one kernel (one star, one realisation, or one
+ *    hyper-parameter grid point).  Batches are described CSR-style:
+ *      n_off[B+1]  offsets of sequence b's samples in y / diag / out          (HOST int64)
+ *      t_off[B]    offset of sequence b's time stamps in t (sequences may share t) (HOST int64)
+ *      j_off[B+1]  offsets of sequence b's complex terms in coef               (HOST int64)
+ *    coef is [sum Jc][4] = (a', b', c, d) per complex term, already exposure-integrated
+ *    (TermConvolution coefficients); ddiag[B] is the constant added to the diagonal.
+ *    A real term (a, c) is passed as the complex term (a, 0, c, 0).
+ *    The state width of sequence b is J_b = 2 * (j_off[b+1] - j_off[b]).
+ *  - Bulk pointers (t, y, diag, coef, ddiag, normals and all outputs) may each be a
+ *    device pointer or a host pointer; the library classifies every pointer with
+ *    cudaPointerGetAttributes and stages host buffers through its own device scratch
+ *    (cudaMemcpyAsync on the handle's stream).  The three offset arrays are always host.
+ *  - Return value: 0 = ok; < 0 = argument error (GF_E_*); > 0 = cudaError_t.
+ *    gf_last_error() gives a message.  Per-sequence numeric failure (non-positive pivot)
+ *    is reported in status[b] = 1 + index of the first d[n] <= 0, 0 if none -- the
+ *    condition on which celerite2 raises LinAlgError (reference gadfly/gp.py:188-192).
+ *  - No global state except the handle; one CUDA stream per handle; calls on one handle
+ *    are serialised by the caller.  Entry points return after the work has completed
+ *    (outputs valid), unless GF_FLAG_ASYNC is set, in which case outputs that are device
+ *    pointers are valid after gf_synchronize().
+ */
+#ifndef GADFLY_B200_H
+#define GADFLY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gf_context *gf_handle;
+
+enum {
+    GF_OK = 0,
+    GF_E_ARG = -1,        /* null / inconsistent argument */
+    GF_E_UNSORTED = -2,   /* reserved */
+    GF_E_TOO_WIDE = -3,   /* J_b exceeds GF_MAX_J */
+    GF_E_NOMEM = -4
+};
+
+/* widest state the register-resident scan supports (22 blocks of 8) */
+#define GF_MAX_J 176
+
+/* flags */
+#define GF_FLAG_ASYNC 1u          /* do not synchronise before returning */
+#define GF_FLAG_REFERENCE_ORDER 2u /* use the simple reference-order scan kernel (validation) */
+
+/* ---- lifetime --------------------------------------------------------------------- */
+int gf_create(int device, gf_handle *out);
+int gf_destroy(gf_handle h);
+int gf_synchronize(gf_handle h);
+const char *gf_last_error(gf_handle h);
+/* the handle's stream as a cudaStream_t (so callers can record events on it) */
+void *gf_stream(gf_handle h);
+/* SM count, measured FP64 FMA peak [flop/s] from a DFMA microbenchmark (0 if !measure) */
+int gf_device_info(gf_handle h, int *sm_count, double *fp64_flops, int measure);
+/* kernels launched by this handle since creation (the bench's gpu_launches claim) */
+int64_t gf_launch_count(gf_handle h);
+/* device time [ms] of the most recent scan / psd kernel launch, from CUDA events recorded
+ * on the handle's stream around the launch (valid after the call returned / synchronised) */
+float gf_last_kernel_ms(gf_handle h);
+
+/* ---- K1: fused factor + forward solve -> log-likelihood pieces ---------------------
+ * Replaces, per sequence: celerite2 GaussianProcess.compute (driver.factor; reference
+ * gadfly/gp.py:59,202-204) followed by log_likelihood (driver.solve_lower; reference
+ * gadfly/gp.py:350):   logdet[b] = sum_n log d_n ,  quad[b] = sum_n z_n^2 / d_n  with
+ * z = L^-1 y.  log L = -(quad + logdet + N log 2 pi) / 2 is formed by the caller.
+ * Nothing of size N*J is materialised. */
+int gf_loglike_batched(gf_handle h, int64_t B, const int64_t *n_off, const int64_t *t_off,
+                       const int64_t *j_off, const double *t, int64_t t_len, const double *y,
+                       const double *diag /* nullable */, const double *coef,
+                       const double *ddiag, double *logdet, double *quad, int32_t *status,
+                       uint32_t flags);
+
+/* ---- K2: fused factor + lower-triangular dot -> samples ----------------------------
+ * Replaces celerite2 GaussianProcess.compute + dot_tril / sample (driver.factor +
+ * driver.matmul_lower; reference gadfly/gp.py:327,391):  out = L_c (sqrt(d) o n).
+ * normals == NULL: n is drawn inside the kernel from Philox4x32-10 keyed by (seed), counter
+ * (sample index / 2, global sequence id seq0 + b, stream), Box-Muller on two 53-bit uniforms
+ * (reproducible on the host: see gadfly_b200/philox.py).  normals != NULL: n is read, laid out
+ * like out.  logdet (nullable) also receives sum log d. */
+int gf_sample_batched(gf_handle h, int64_t B, const int64_t *n_off, const int64_t *t_off,
+                      const int64_t *j_off, const double *t, int64_t t_len,
+                      const double *diag /* nullable */, const double *coef,
+                      const double *ddiag, const double *normals /* nullable */, uint64_t seed,
+                      uint64_t seq0, double *out, double *logdet /* nullable */,
+                      int32_t *status, uint32_t flags);
+
+/* ---- K3: factor, materialising d[N] (and W[N,J] if W != NULL) ----------------------
+ * Replaces driver.factor where the factor itself is wanted (reference gadfly/gp.py:202-204
+ * followed by apply_inverse / predict, gadfly/gp.py:370,232).  d is laid out like y;
+ * W is [sum_b N_b * J_b], row-major per sequence, offsets w_off[B] (HOST int64), columns in
+ * celerite2's blocked order [cos-block | sin-block]. */
+int gf_factor_batched(gf_handle h, int64_t B, const int64_t *n_off, const int64_t *t_off,
+                      const int64_t *j_off, const int64_t *w_off, const double *t, int64_t t_len,
+                      const double *diag /* nullable */, const double *coef,
+                      const double *ddiag, double *d, double *W /* nullable */,
+                      double *logdet, int32_t *status, uint32_t flags);
+
+/* ---- K4: O(N J) sweeps on a stored factor -----------------------------------------
+ * Replaces driver.solve_lower / matmul_lower / solve_upper / matmul_upper (reference
+ * gadfly/gp.py:327,350,370).  op: 0 solve_lower (Z = L^-1 Y), 1 matmul_lower (Z = L Y),
+ * 2 solve_upper (Z = L^-T Y), 3 matmul_upper (Z = L^T Y).  Y and Z are [N] per sequence,
+ * laid out like y; Z may alias Y.  U rows are regenerated from (t, coef) on the fly. */
+int gf_sweep_batched(gf_handle h, int op, int64_t B, const int64_t *n_off, const int64_t *t_off,
+                     const int64_t *j_off, const int64_t *w_off, const double *t, int64_t t_len,
+                     const double *coef, const double *W, const double *Y, double *Z,
+                     uint32_t flags);
+
+/* ---- K5: kernel power spectral density on a dense frequency grid -------------------
+ * Replaces celerite2 Term.get_psd / TermConvolution.get_psd (reference gadfly/psd.py:151,
+ * gadfly/tests/test_core.py:34; closed form gadfly/core.py:33-41):
+ *   out[b][f] = sqrt(2/pi) sum_j ((a c + b d)(c^2+d^2) + (a c - b d) w^2)
+ *                                / (w^4 + 2 (c^2 - d^2) w^2 + (c^2+d^2)^2)  * sinc^2(delta_b w / 2)
+ * with the UN-convolved coefficients coef_base[sum Jc][4] and w = omega[f], shared by all b. */
+int gf_psd_batched(gf_handle h, int64_t B, const int64_t *j_off, const double *coef_base,
+                   const double *delta /* [B] */, const double *omega, int64_t F,
+                   double *out /* [B][F] */, uint32_t flags);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GADFLY_B200_H */
