@@ -4,3 +4,7 @@ __version__ = "0.1.0"
 from . import units  # noqa: F401
 from .core import *  # noqa: F401,F403
 from .terms import *  # noqa: F401,F403
+from .gp import *  # noqa: F401,F403
+from .psd import *  # noqa: F401,F403
+from .solver import Solver, KernelBatch, LinAlgError, SolverUnavailable  # noqa: F401
+from . import batch  # noqa: F401

@@ -1,0 +1,133 @@
+"""
+Batched GP work on independent light curves / kernels, and its sharding across GPUs.
+
+The reference has no batch interface (it loops a Python ``GaussianProcess`` per star:
+notebooks/paper/runtime-speed.ipynb:40-42); these helpers are the same calls
+(``compute`` + ``log_likelihood``, ``compute`` + ``sample``, ``kernel.get_psd``) issued for
+B independent units at once through the fused CUDA kernels, which materialise nothing of
+size N*J.  Units are independent, so multi-GPU is pure sharding: rank r owns a contiguous
+block of units (balanced by N*J^2), and the only collective is the final gather of the
+per-unit scalars.
+"""
+import numpy as np
+
+from .solver import Geometry, KernelBatch, default_solver
+
+__all__ = ['log_likelihood', 'sample', 'shard_bounds', 'shard', 'gather_concat']
+
+_LOG_2PI = float(np.log(2 * np.pi))
+
+
+def _as_batch(kernels):
+    return kernels if isinstance(kernels, KernelBatch) else KernelBatch(kernels)
+
+
+def _geometry(kb, t, lengths):
+    if lengths is None:
+        t = np.asarray(t) if not hasattr(t, 'data_ptr') else t
+        if hasattr(t, 'data_ptr') or t.ndim == 1:
+            N = t.numel() if hasattr(t, 'data_ptr') else t.shape[0]
+            return Geometry.shared_t(kb.B, int(N))
+        assert t.shape[0] == kb.B
+        return Geometry.ragged([t.shape[1]] * kb.B)
+    return Geometry.ragged(lengths)
+
+
+def log_likelihood(kernels, t, y, diag=None, lengths=None, mean=0.0, quiet=True, solver=None,
+                   return_parts=False, flags=0):
+    """log-likelihood of B light curves under B kernels.
+
+    ``t``: ``[N]`` (one cadence shared by all units), ``[B, N]``, or a flat concatenation
+    with ``lengths``;  ``y``, ``diag``: ``[B, N]`` or flat.  Non-positive-definite units give
+    ``-inf`` (``quiet=True``) or raise ``LinAlgError``."""
+    from .solver import LinAlgError
+    kb = _as_batch(kernels)
+    geom = _geometry(kb, t, lengths)
+    solver = solver or default_solver()
+    if not hasattr(y, 'data_ptr'):
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        if np.any(mean != 0.0):
+            y = y - mean
+    logdet, quad, status = solver.loglike(kb, geom, t, y, diag, flags=flags)
+    N = np.diff(geom.n_off)
+    ll = -0.5 * (quad + logdet + N * _LOG_2PI)
+    bad = status != 0
+    if np.any(bad):
+        if not quiet:
+            b = int(np.flatnonzero(bad)[0])
+            raise LinAlgError(f"unit {b}: failed to factorize, d[{status[b] - 1}] <= 0")
+        ll = np.where(bad, -np.inf, ll)
+    if return_parts:
+        return ll, logdet, quad, status
+    return ll
+
+
+def sample(kernels, t, diag=None, lengths=None, normals=None, seed=0, seq0=0, solver=None,
+           subtract_mean=True, out=None, flags=0):
+    """One GP draw per unit: ``x = L (sqrt(d) o n)``.  ``normals=None`` draws n on the device
+    from Philox4x32-10 keyed by ``seed`` and the global unit index ``seq0 + b``
+    (reproducible on the host with :mod:`gadfly_b200.philox`).  ``subtract_mean`` applies the
+    reference's per-draw mean subtraction (gadfly/gp.py:392)."""
+    kb = _as_batch(kernels)
+    geom = _geometry(kb, t, lengths)
+    solver = solver or default_solver()
+    x, logdet, status = solver.sample(kb, geom, t, diag, normals, seed=seed, seq0=seq0, out=out,
+                                      flags=flags)
+    if hasattr(x, 'data_ptr'):
+        return x, status
+    rows = [x[geom.n_off[b]:geom.n_off[b + 1]] for b in range(kb.B)]
+    if subtract_mean:
+        for r in rows:
+            if len(r):
+                r -= r.mean()
+    if lengths is None:
+        return x.reshape(kb.B, -1), status
+    return rows, status
+
+
+# ---- sharding -------------------------------------------------------------------------
+def shard_bounds(cost, world):
+    """Contiguous block boundaries [world+1] that balance ``sum(cost)`` per rank."""
+    cost = np.asarray(cost, dtype=np.float64)
+    B = len(cost)
+    if B == 0:
+        return np.zeros(world + 1, dtype=np.int64)
+    csum = np.concatenate([[0.0], np.cumsum(cost)])
+    targets = csum[-1] * np.arange(1, world) / world
+    cuts = np.searchsorted(csum, targets, side='left')
+    # pick the closer of the two neighbouring cut points
+    cuts = np.where((cuts > 0) & (np.abs(csum[np.maximum(cuts - 1, 0)] - targets)
+                                  < np.abs(csum[np.minimum(cuts, B)] - targets)), cuts - 1, cuts)
+    bounds = np.concatenate([[0], np.clip(cuts, 0, B), [B]]).astype(np.int64)
+    return np.maximum.accumulate(bounds)
+
+
+def shard(B, rank, world, cost=None):
+    """Index range [lo, hi) of the units rank ``rank`` owns."""
+    if cost is None:
+        cost = np.ones(B)
+    b = shard_bounds(cost, world)
+    return int(b[rank]), int(b[rank + 1])
+
+
+def gather_concat(local, bounds=None, group=None):
+    """All-gather per-unit results (1-D float64/int32 arrays of per-rank length) into the full
+    array on every rank: the only collective of the path.  NCCL for CUDA tensors / when the
+    process group is NCCL, gloo otherwise."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return np.asarray(local)
+    world = dist.get_world_size(group)
+    backend = dist.get_backend(group)
+    dev = torch.device('cuda', torch.cuda.current_device()) if backend == 'nccl' else torch.device('cpu')
+    x = torch.as_tensor(np.ascontiguousarray(local)).to(dev)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([x.numel()], dtype=torch.int64, device=dev), group=group)
+    sizes = [int(s.item()) for s in sizes]
+    m = max(sizes) if sizes else 0
+    pad = torch.zeros(m, dtype=x.dtype, device=dev)
+    pad[:x.numel()] = x
+    parts = [torch.empty(m, dtype=x.dtype, device=dev) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    return torch.cat([p[:s] for p, s in zip(parts, sizes)]).cpu().numpy()

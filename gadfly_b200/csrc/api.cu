@@ -1,0 +1,457 @@
+// C ABI of the gadfly_b200 CUDA library (see include/gadfly_b200.h for the contract).
+//
+// Everything here is host-side plumbing: pointer classification and staging, batch
+// descriptors, the heaviest-first work order, launch bookkeeping.  The arithmetic is in
+// scan_fast.cu / scan_ref.cu (O(N J^2) scans), sweep.cu (O(N J) sweeps) and psd.cu.
+#include "../../include/gadfly_b200.h"
+#include "common.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <numeric>
+#include <string>
+#include <vector>
+
+namespace gf {
+cudaError_t launch_scan_ref(int mode, const ScanArgs &args, int grid, cudaStream_t stream);
+cudaError_t launch_scan_fast(int mode, const ScanArgs &args, int jmax, int sm_count,
+                             cudaStream_t stream, int *launches);
+bool scan_fast_supports(int mode, int jmax);
+cudaError_t launch_sweep(int op, int64_t B, const int64_t *n_off, const int64_t *t_off,
+                         const int64_t *j_off, const int64_t *w_off, const double *t,
+                         const double *coef, const double *W, const double *Y, double *Z,
+                         cudaStream_t stream);
+cudaError_t launch_psd(int64_t B, const int64_t *j_off, const double *coef, const double *delta,
+                       const double *omega, int64_t F, double *out, cudaStream_t stream);
+cudaError_t measure_fp64_peak(int sm_count, cudaStream_t stream, double *flops);
+}  // namespace gf
+
+namespace {
+
+enum Slot {
+    S_NOFF, S_TOFF, S_JOFF, S_WOFF, S_ORDER, S_COUNTER, S_T, S_Y, S_DIAG, S_COEF, S_DDIAG,
+    S_OUT, S_OUTW, S_LOGDET, S_QUAD, S_STATUS, S_OMEGA, S_DELTA, S_W, N_SLOTS
+};
+
+struct Buf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace
+
+struct gf_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int sm_count = 0;
+    double fp64_flops = 0.0;
+    int64_t launches = 0;
+    bool timed = false;
+    std::string err;
+    Buf buf[N_SLOTS];
+};
+
+namespace {
+
+struct Guard {
+    int prev = -1;
+    explicit Guard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); }
+    ~Guard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int fail(gf_handle h, int code, const char *what)
+{
+    if (h) {
+        h->err = what;
+        if (code > 0) { h->err += ": "; h->err += cudaGetErrorString((cudaError_t)code); }
+    }
+    return code;
+}
+
+#define GF_CUDA(h, expr)                                                      \
+    do {                                                                      \
+        cudaError_t e__ = (expr);                                             \
+        if (e__ != cudaSuccess) return fail((h), (int)e__, #expr);            \
+    } while (0)
+
+bool is_device_ptr(const void *p)
+{
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+cudaError_t reserve(gf_handle h, int slot, size_t bytes)
+{
+    Buf &b = h->buf[slot];
+    if (bytes <= b.cap) return cudaSuccess;
+    if (b.p) {
+        cudaError_t e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) return e;
+        cudaFree(b.p);
+        b.p = nullptr; b.cap = 0;
+    }
+    size_t cap = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, cap);
+    if (e != cudaSuccess) { b.p = nullptr; return e; }
+    b.cap = cap;
+    return cudaSuccess;
+}
+
+// Input that may live on the host: returns a device pointer valid on h->stream.
+template <typename T>
+cudaError_t stage_in(gf_handle h, int slot, const T *src, size_t count, const T **dev)
+{
+    if (!src || count == 0) { *dev = src; return cudaSuccess; }
+    if (is_device_ptr(src)) { *dev = src; return cudaSuccess; }
+    cudaError_t e = reserve(h, slot, count * sizeof(T));
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyAsync(h->buf[slot].p, src, count * sizeof(T), cudaMemcpyHostToDevice, h->stream);
+    *dev = (const T *)h->buf[slot].p;
+    return e;
+}
+
+// Output that may live on the host: device pointer now, copy back later.
+template <typename T>
+struct Out {
+    T *user = nullptr;
+    T *dev = nullptr;
+    size_t count = 0;
+    bool host = false;
+};
+
+template <typename T>
+cudaError_t stage_out(gf_handle h, int slot, T *dst, size_t count, Out<T> *o)
+{
+    o->user = dst; o->count = count; o->host = false; o->dev = dst;
+    if (!dst || count == 0) return cudaSuccess;
+    if (is_device_ptr(dst)) return cudaSuccess;
+    cudaError_t e = reserve(h, slot, count * sizeof(T));
+    if (e != cudaSuccess) return e;
+    o->dev = (T *)h->buf[slot].p;
+    o->host = true;
+    return cudaSuccess;
+}
+
+template <typename T>
+cudaError_t finish_out(gf_handle h, const Out<T> &o)
+{
+    if (!o.host || !o.user || o.count == 0) return cudaSuccess;
+    return cudaMemcpyAsync(o.user, o.dev, o.count * sizeof(T), cudaMemcpyDeviceToHost, h->stream);
+}
+
+// Batch geometry shared by the scan entry points.
+struct Geometry {
+    int64_t total_n = 0;   // n_off[B]
+    int64_t total_j = 0;   // j_off[B]
+    int jmax = 0;          // widest state in the batch
+    std::vector<int32_t> order;
+};
+
+int check_geometry(gf_handle h, int64_t B, const int64_t *n_off, const int64_t *t_off,
+                   const int64_t *j_off, int64_t t_len, Geometry *g)
+{
+    if (!h) return GF_E_ARG;
+    if (B < 0 || (B > 0 && (!n_off || !t_off || !j_off))) return fail(h, GF_E_ARG, "null batch descriptor");
+    if (B > 0x7fffffff) return fail(h, GF_E_ARG, "batch too large");
+    g->order.resize((size_t)B);
+    std::vector<double> cost((size_t)B);
+    for (int64_t b = 0; b < B; ++b) {
+        int64_t N = n_off[b + 1] - n_off[b];
+        int64_t Jc = j_off[b + 1] - j_off[b];
+        if (N < 0 || Jc < 0) return fail(h, GF_E_ARG, "offsets must be non-decreasing");
+        if (2 * Jc > GF_MAX_J) return fail(h, GF_E_TOO_WIDE, "state wider than GF_MAX_J");
+        if (t_off[b] < 0 || t_off[b] + N > t_len) return fail(h, GF_E_ARG, "t_off out of range");
+        g->jmax = std::max(g->jmax, (int)(2 * Jc));
+        cost[(size_t)b] = (double)N * (double)(4 * Jc * Jc + 8);
+        g->order[(size_t)b] = (int32_t)b;
+    }
+    if (B > 0) {
+        if (n_off[0] != 0 || j_off[0] < 0) return fail(h, GF_E_ARG, "offsets must start at 0");
+        g->total_n = n_off[B];
+        g->total_j = j_off[B];
+    }
+    // heaviest first: the persistent CTAs pull sequences from a queue
+    std::stable_sort(g->order.begin(), g->order.end(),
+                     [&](int32_t a, int32_t b) { return cost[(size_t)a] > cost[(size_t)b]; });
+    return GF_OK;
+}
+
+struct Timer {
+    gf_handle h;
+    explicit Timer(gf_handle h_) : h(h_) { cudaEventRecord(h->ev0, h->stream); }
+    ~Timer() { cudaEventRecord(h->ev1, h->stream); h->timed = true; }
+};
+
+int run_scan(gf_handle h, int mode, int64_t B, const int64_t *n_off, const int64_t *t_off,
+             const int64_t *j_off, const int64_t *w_off, const double *t, int64_t t_len,
+             const double *y, const double *diag, const double *coef, const double *ddiag,
+             uint64_t seed, uint64_t seq0, double *out_x, double *out_W, int64_t w_len,
+             double *logdet, double *quad, int32_t *status, uint32_t flags)
+{
+    Geometry g;
+    int rc = check_geometry(h, B, n_off, t_off, j_off, t_len, &g);
+    if (rc != GF_OK) return rc;
+    if (B == 0) return GF_OK;
+    if (!t || !coef || !ddiag || !status) return fail(h, GF_E_ARG, "null data pointer");
+    Guard guard(h->device);
+
+    gf::ScanArgs A;
+    std::memset(&A, 0, sizeof(A));
+    A.B = B;
+    GF_CUDA(h, stage_in(h, S_NOFF, n_off, (size_t)B + 1, &A.n_off));
+    GF_CUDA(h, stage_in(h, S_TOFF, t_off, (size_t)B, &A.t_off));
+    GF_CUDA(h, stage_in(h, S_JOFF, j_off, (size_t)B + 1, &A.j_off));
+    if (w_off) GF_CUDA(h, stage_in(h, S_WOFF, w_off, (size_t)B, &A.w_off));
+    const int32_t *order_dev = nullptr;
+    GF_CUDA(h, stage_in(h, S_ORDER, (const int32_t *)g.order.data(), (size_t)B, &order_dev));
+    A.order = order_dev;
+    GF_CUDA(h, reserve(h, S_COUNTER, sizeof(int)));
+    A.counter = (int *)h->buf[S_COUNTER].p;
+    GF_CUDA(h, cudaMemsetAsync(A.counter, 0, sizeof(int), h->stream));
+    GF_CUDA(h, stage_in(h, S_T, t, (size_t)t_len, &A.t));
+    GF_CUDA(h, stage_in(h, S_Y, y, (size_t)g.total_n, &A.y));
+    GF_CUDA(h, stage_in(h, S_DIAG, diag, (size_t)g.total_n, &A.diag));
+    GF_CUDA(h, stage_in(h, S_COEF, coef, (size_t)g.total_j * 4, &A.coef));
+    GF_CUDA(h, stage_in(h, S_DDIAG, ddiag, (size_t)B, &A.ddiag));
+    A.seed = seed;
+    A.seq0 = seq0;
+
+    Out<double> o_x, o_W, o_ld, o_q;
+    Out<int32_t> o_st;
+    GF_CUDA(h, stage_out(h, S_OUT, out_x, (size_t)g.total_n, &o_x));
+    GF_CUDA(h, stage_out(h, S_OUTW, out_W, (size_t)w_len, &o_W));
+    GF_CUDA(h, stage_out(h, S_LOGDET, logdet, (size_t)B, &o_ld));
+    GF_CUDA(h, stage_out(h, S_QUAD, quad, (size_t)B, &o_q));
+    GF_CUDA(h, stage_out(h, S_STATUS, status, (size_t)B, &o_st));
+    A.out_x = o_x.dev; A.out_W = o_W.dev; A.quad = o_q.dev; A.status = o_st.dev;
+    // the kernels always write logdet: give them scratch when the caller does not want it
+    if (!o_ld.dev) {
+        GF_CUDA(h, reserve(h, S_LOGDET, (size_t)B * sizeof(double)));
+        A.logdet = (double *)h->buf[S_LOGDET].p;
+    } else {
+        A.logdet = o_ld.dev;
+    }
+
+    {
+        Timer timer(h);
+        const bool ref = (flags & GF_FLAG_REFERENCE_ORDER) || !gf::scan_fast_supports(mode, g.jmax);
+        if (ref) {
+            int grid = (int)std::min<int64_t>(B, (int64_t)h->sm_count);
+            GF_CUDA(h, gf::launch_scan_ref(mode, A, grid, h->stream));
+            h->launches += 1;
+        } else {
+            int n = 0;
+            GF_CUDA(h, gf::launch_scan_fast(mode, A, g.jmax, h->sm_count, h->stream, &n));
+            h->launches += n;
+        }
+    }
+
+    GF_CUDA(h, finish_out(h, o_x));
+    GF_CUDA(h, finish_out(h, o_W));
+    GF_CUDA(h, finish_out(h, o_ld));
+    GF_CUDA(h, finish_out(h, o_q));
+    GF_CUDA(h, finish_out(h, o_st));
+    if (!(flags & GF_FLAG_ASYNC)) GF_CUDA(h, cudaStreamSynchronize(h->stream));
+    return GF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gf_create(int device, gf_handle *out)
+{
+    if (!out) return GF_E_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess) return (int)e;
+    if (device < 0 || device >= count) return GF_E_ARG;
+    gf_context *h = new (std::nothrow) gf_context;
+    if (!h) return GF_E_NOMEM;
+    h->device = device;
+    Guard guard(device);
+    e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) { delete h; return (int)e; }
+    *out = h;
+    return GF_OK;
+}
+
+int gf_destroy(gf_handle h)
+{
+    if (!h) return GF_OK;
+    Guard guard(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (auto &b : h->buf) if (b.p) cudaFree(b.p);
+    cudaEventDestroy(h->ev0);
+    cudaEventDestroy(h->ev1);
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return GF_OK;
+}
+
+int gf_synchronize(gf_handle h)
+{
+    if (!h) return GF_E_ARG;
+    Guard guard(h->device);
+    GF_CUDA(h, cudaStreamSynchronize(h->stream));
+    return GF_OK;
+}
+
+const char *gf_last_error(gf_handle h) { return h ? h->err.c_str() : "null handle"; }
+
+void *gf_stream(gf_handle h) { return h ? (void *)h->stream : nullptr; }
+
+int gf_device_info(gf_handle h, int *sm_count, double *fp64_flops, int measure)
+{
+    if (!h) return GF_E_ARG;
+    Guard guard(h->device);
+    if (sm_count) *sm_count = h->sm_count;
+    if (measure && h->fp64_flops == 0.0) {
+        GF_CUDA(h, gf::measure_fp64_peak(h->sm_count, h->stream, &h->fp64_flops));
+        h->launches += 4;
+    }
+    if (fp64_flops) *fp64_flops = h->fp64_flops;
+    return GF_OK;
+}
+
+int64_t gf_launch_count(gf_handle h) { return h ? h->launches : 0; }
+
+float gf_last_kernel_ms(gf_handle h)
+{
+    if (!h || !h->timed) return 0.0f;
+    Guard guard(h->device);
+    float ms = 0.0f;
+    if (cudaEventSynchronize(h->ev1) != cudaSuccess) return 0.0f;
+    if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) != cudaSuccess) return 0.0f;
+    return ms;
+}
+
+int gf_loglike_batched(gf_handle h, int64_t B, const int64_t *n_off, const int64_t *t_off,
+                       const int64_t *j_off, const double *t, int64_t t_len, const double *y,
+                       const double *diag, const double *coef, const double *ddiag,
+                       double *logdet, double *quad, int32_t *status, uint32_t flags)
+{
+    if (!h) return GF_E_ARG;
+    if (B > 0 && (!y || !logdet || !quad)) return fail(h, GF_E_ARG, "null data pointer");
+    return run_scan(h, gf::MODE_LOGLIKE, B, n_off, t_off, j_off, nullptr, t, t_len, y, diag, coef,
+                    ddiag, 0, 0, nullptr, nullptr, 0, logdet, quad, status, flags);
+}
+
+int gf_sample_batched(gf_handle h, int64_t B, const int64_t *n_off, const int64_t *t_off,
+                      const int64_t *j_off, const double *t, int64_t t_len, const double *diag,
+                      const double *coef, const double *ddiag, const double *normals,
+                      uint64_t seed, uint64_t seq0, double *out, double *logdet, int32_t *status,
+                      uint32_t flags)
+{
+    if (!h) return GF_E_ARG;
+    if (B > 0 && !out) return fail(h, GF_E_ARG, "null output pointer");
+    return run_scan(h, gf::MODE_SAMPLE, B, n_off, t_off, j_off, nullptr, t, t_len, normals, diag,
+                    coef, ddiag, seed, seq0, out, nullptr, 0, logdet, nullptr, status, flags);
+}
+
+int gf_factor_batched(gf_handle h, int64_t B, const int64_t *n_off, const int64_t *t_off,
+                      const int64_t *j_off, const int64_t *w_off, const double *t, int64_t t_len,
+                      const double *diag, const double *coef, const double *ddiag, double *d,
+                      double *W, double *logdet, int32_t *status, uint32_t flags)
+{
+    if (!h) return GF_E_ARG;
+    if (B > 0 && !d) return fail(h, GF_E_ARG, "null output pointer");
+    if (W && !w_off) return fail(h, GF_E_ARG, "W needs w_off");
+    int64_t w_len = 0;
+    if (W && B > 0 && n_off && j_off)
+        for (int64_t b = 0; b < B; ++b)
+            w_len = std::max(w_len, w_off[b] + (n_off[b + 1] - n_off[b]) * 2 * (j_off[b + 1] - j_off[b]));
+    return run_scan(h, gf::MODE_FACTOR, B, n_off, t_off, j_off, W ? w_off : nullptr, t, t_len,
+                    nullptr, diag, coef, ddiag, 0, 0, d, W, w_len, logdet, nullptr, status, flags);
+}
+
+int gf_sweep_batched(gf_handle h, int op, int64_t B, const int64_t *n_off, const int64_t *t_off,
+                     const int64_t *j_off, const int64_t *w_off, const double *t, int64_t t_len,
+                     const double *coef, const double *W, const double *Y, double *Z,
+                     uint32_t flags)
+{
+    if (!h) return GF_E_ARG;
+    if (op < 0 || op > 3) return fail(h, GF_E_ARG, "op must be 0..3");
+    Geometry g;
+    int rc = check_geometry(h, B, n_off, t_off, j_off, t_len, &g);
+    if (rc != GF_OK) return rc;
+    if (B == 0) return GF_OK;
+    if (!t || !coef || !W || !Y || !Z || !w_off) return fail(h, GF_E_ARG, "null data pointer");
+    Guard guard(h->device);
+    int64_t w_len = 0;
+    for (int64_t b = 0; b < B; ++b)
+        w_len = std::max(w_len, w_off[b] + (n_off[b + 1] - n_off[b]) * 2 * (j_off[b + 1] - j_off[b]));
+    const int64_t *d_noff, *d_toff, *d_joff, *d_woff;
+    const double *d_t, *d_coef, *d_W, *d_Y;
+    GF_CUDA(h, stage_in(h, S_NOFF, n_off, (size_t)B + 1, &d_noff));
+    GF_CUDA(h, stage_in(h, S_TOFF, t_off, (size_t)B, &d_toff));
+    GF_CUDA(h, stage_in(h, S_JOFF, j_off, (size_t)B + 1, &d_joff));
+    GF_CUDA(h, stage_in(h, S_WOFF, w_off, (size_t)B, &d_woff));
+    GF_CUDA(h, stage_in(h, S_T, t, (size_t)t_len, &d_t));
+    GF_CUDA(h, stage_in(h, S_COEF, coef, (size_t)g.total_j * 4, &d_coef));
+    GF_CUDA(h, stage_in(h, S_W, W, (size_t)w_len, &d_W));
+    Out<double> o_z;
+    // Z may alias Y: stage Y into the same slot the result is produced in
+    if (!is_device_ptr(Z)) {
+        GF_CUDA(h, stage_out(h, S_OUT, Z, (size_t)g.total_n, &o_z));
+        if (!is_device_ptr(Y)) {
+            GF_CUDA(h, cudaMemcpyAsync(o_z.dev, Y, (size_t)g.total_n * sizeof(double),
+                                       cudaMemcpyHostToDevice, h->stream));
+            d_Y = o_z.dev;
+        } else {
+            d_Y = Y;
+        }
+    } else {
+        o_z.dev = Z;
+        GF_CUDA(h, stage_in(h, S_Y, Y, (size_t)g.total_n, &d_Y));
+    }
+    {
+        Timer timer(h);
+        GF_CUDA(h, gf::launch_sweep(op, B, d_noff, d_toff, d_joff, d_woff, d_t, d_coef, d_W, d_Y,
+                                    o_z.dev, h->stream));
+        h->launches += 1;
+    }
+    GF_CUDA(h, finish_out(h, o_z));
+    if (!(flags & GF_FLAG_ASYNC)) GF_CUDA(h, cudaStreamSynchronize(h->stream));
+    return GF_OK;
+}
+
+int gf_psd_batched(gf_handle h, int64_t B, const int64_t *j_off, const double *coef_base,
+                   const double *delta, const double *omega, int64_t F, double *out,
+                   uint32_t flags)
+{
+    if (!h) return GF_E_ARG;
+    if (B < 0 || F < 0) return fail(h, GF_E_ARG, "negative size");
+    if (B == 0 || F == 0) return GF_OK;
+    if (!j_off || !coef_base || !omega || !out) return fail(h, GF_E_ARG, "null data pointer");
+    for (int64_t b = 0; b < B; ++b)
+        if (j_off[b + 1] < j_off[b]) return fail(h, GF_E_ARG, "offsets must be non-decreasing");
+    Guard guard(h->device);
+    const int64_t *d_joff;
+    const double *d_coef, *d_delta, *d_omega;
+    GF_CUDA(h, stage_in(h, S_JOFF, j_off, (size_t)B + 1, &d_joff));
+    GF_CUDA(h, stage_in(h, S_COEF, coef_base, (size_t)j_off[B] * 4, &d_coef));
+    GF_CUDA(h, stage_in(h, S_DELTA, delta, (size_t)B, &d_delta));
+    GF_CUDA(h, stage_in(h, S_OMEGA, omega, (size_t)F, &d_omega));
+    Out<double> o;
+    GF_CUDA(h, stage_out(h, S_OUT, out, (size_t)B * (size_t)F, &o));
+    {
+        Timer timer(h);
+        GF_CUDA(h, gf::launch_psd(B, d_joff, d_coef, d_delta, d_omega, F, o.dev, h->stream));
+        h->launches += (B + 65534) / 65535;
+    }
+    GF_CUDA(h, finish_out(h, o));
+    if (!(flags & GF_FLAG_ASYNC)) GF_CUDA(h, cudaStreamSynchronize(h->stream));
+    return GF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,403 @@
+"""
+ctypes binding of ``libgadfly_b200.so`` -- the C ABI declared in
+``include/gadfly_b200.h`` -- plus the batch descriptors the library consumes.
+
+This module is the only place the Python facade touches the GPU.  There is no
+CPU fallback: if the shared library is missing or no CUDA device is visible,
+every entry point raises :class:`SolverUnavailable`.
+
+The functions mirror what gadfly reaches through celerite2 (reference call
+sites in parentheses):
+
+=====================  ==========================================================
+``Solver.loglike``     ``GaussianProcess.compute`` + ``log_likelihood``
+                       (gadfly/gp.py:59,202-204,350), fused, nothing materialised
+``Solver.sample``      ``compute`` + ``dot_tril``/``sample`` (gadfly/gp.py:327,391)
+``Solver.factor``      ``compute`` keeping d and W (gadfly/gp.py:202-204)
+``Solver.sweep``       ``driver.solve_lower/matmul_lower/solve_upper/matmul_upper``
+                       (gadfly/gp.py:327,350,370)
+``Solver.psd``         ``kernel.get_psd`` (gadfly/psd.py:151, tests/test_core.py:34)
+=====================  ==========================================================
+"""
+import ctypes
+import os
+import threading
+
+import numpy as np
+
+__all__ = ["Solver", "KernelBatch", "SolverUnavailable", "LinAlgError", "default_solver",
+           "library_path", "GF_MAX_J", "FLAG_ASYNC", "FLAG_REFERENCE_ORDER"]
+
+GF_MAX_J = 176
+FLAG_ASYNC = 1
+FLAG_REFERENCE_ORDER = 2
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBNAME = "libgadfly_b200.so"
+
+
+class SolverUnavailable(RuntimeError):
+    """The CUDA library (or a CUDA device) is not available; there is no CPU fallback."""
+
+
+class LinAlgError(Exception):
+    """The covariance matrix is not positive definite (a pivot d[n] <= 0);
+    celerite2 raises ``driver.LinAlgError`` in the same situation."""
+
+
+def library_path():
+    return os.path.join(_HERE, _LIBNAME)
+
+
+_lib = None
+_lib_lock = threading.Lock()
+
+_i64p = ctypes.POINTER(ctypes.c_int64)
+_f64p = ctypes.c_void_p      # host or device address
+_i32p = ctypes.c_void_p
+
+# name -> (restype, argtypes); must list every symbol include/gadfly_b200.h declares
+_SIGNATURES = {
+    "gf_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
+    "gf_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "gf_synchronize": (ctypes.c_int, [ctypes.c_void_p]),
+    "gf_last_error": (ctypes.c_char_p, [ctypes.c_void_p]),
+    "gf_stream": (ctypes.c_void_p, [ctypes.c_void_p]),
+    "gf_device_info": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int),
+                                      ctypes.POINTER(ctypes.c_double), ctypes.c_int]),
+    "gf_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),
+    "gf_last_kernel_ms": (ctypes.c_float, [ctypes.c_void_p]),
+    "gf_loglike_batched": (ctypes.c_int, [
+        ctypes.c_void_p, ctypes.c_int64, _i64p, _i64p, _i64p, _f64p, ctypes.c_int64, _f64p, _f64p,
+        _f64p, _f64p, _f64p, _f64p, _i32p, ctypes.c_uint32]),
+    "gf_sample_batched": (ctypes.c_int, [
+        ctypes.c_void_p, ctypes.c_int64, _i64p, _i64p, _i64p, _f64p, ctypes.c_int64, _f64p, _f64p,
+        _f64p, _f64p, ctypes.c_uint64, ctypes.c_uint64, _f64p, _f64p, _i32p, ctypes.c_uint32]),
+    "gf_factor_batched": (ctypes.c_int, [
+        ctypes.c_void_p, ctypes.c_int64, _i64p, _i64p, _i64p, _i64p, _f64p, ctypes.c_int64, _f64p,
+        _f64p, _f64p, _f64p, _f64p, _f64p, _i32p, ctypes.c_uint32]),
+    "gf_sweep_batched": (ctypes.c_int, [
+        ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, _i64p, _i64p, _i64p, _i64p, _f64p,
+        ctypes.c_int64, _f64p, _f64p, _f64p, _f64p, ctypes.c_uint32]),
+    "gf_psd_batched": (ctypes.c_int, [
+        ctypes.c_void_p, ctypes.c_int64, _i64p, _f64p, _f64p, _f64p, ctypes.c_int64, _f64p,
+        ctypes.c_uint32]),
+}
+
+
+def load_library(path=None):
+    """dlopen the C-ABI library and bind every declared symbol (no GPU needed for this)."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None and path is None:
+            return _lib
+        path = path or library_path()
+        if not os.path.exists(path):
+            raise SolverUnavailable(
+                f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; "
+                f"g.build()'` (nvcc, sm_100a). gadfly_b200 has no CPU fallback.")
+        try:
+            L = ctypes.CDLL(path)
+        except OSError as exc:  # pragma: no cover - e.g. libcudart missing
+            raise SolverUnavailable(f"cannot load {path}: {exc}") from exc
+        for name, (restype, argtypes) in _SIGNATURES.items():
+            fn = getattr(L, name)   # AttributeError if the header and the library disagree
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = L
+        return L
+
+
+# ---------------------------------------------------------------------------------------
+# pointers: numpy arrays (host) or anything with ``data_ptr()`` (a torch CUDA/CPU tensor)
+# ---------------------------------------------------------------------------------------
+def _addr(x, dtype=np.float64, count=None, name="array"):
+    """(address, keepalive) of a contiguous float64/int32 buffer on host or device."""
+    if x is None:
+        return None, None
+    if hasattr(x, "data_ptr"):  # torch tensor
+        import torch
+        want = {np.float64: torch.float64, np.int32: torch.int32, np.int64: torch.int64}[dtype]
+        if x.dtype != want or not x.is_contiguous():
+            raise TypeError(f"{name}: tensor must be contiguous {want}")
+        if count is not None and x.numel() < count:
+            raise ValueError(f"{name}: {x.numel()} elements, need {count}")
+        return x.data_ptr(), x
+    a = np.ascontiguousarray(x, dtype=dtype)
+    if count is not None and a.size < count:
+        raise ValueError(f"{name}: {a.size} elements, need {count}")
+    return a.ctypes.data, a
+
+
+def _out(x, shape, dtype=np.float64):
+    """An output buffer: the caller's (tensor or ndarray, written in place) or a new ndarray."""
+    if x is None:
+        x = np.empty(shape, dtype=dtype)
+    elif not hasattr(x, "data_ptr"):
+        if not (isinstance(x, np.ndarray) and x.dtype == dtype and x.flags.c_contiguous):
+            raise TypeError("output must be a C-contiguous ndarray of the right dtype")
+    addr, keep = _addr(x, dtype, int(np.prod(shape)))
+    return x, addr
+
+
+def _i64(a):
+    a = np.ascontiguousarray(a, dtype=np.int64)
+    return a, a.ctypes.data_as(_i64p)
+
+
+class KernelBatch:
+    """Flat coefficient arrays of B kernels, as the library wants them.
+
+    ``coef``  [sum Jc, 4]  (a', b', c, d) of every complex term after the exposure-time
+                           transform (real terms enter as (a, 0, c, 0));
+    ``base``  [sum Jc, 4]  the un-convolved coefficients (PSD);
+    ``j_off`` [B+1], ``ddiag`` [B], ``delta`` [B].
+    """
+
+    def __init__(self, kernels):
+        kernels = list(kernels)
+        coef, base, j_off, ddiag, delta = [], [], [0], [], []
+        for k in kernels:
+            ar, cr, ac, bc, cc, dc, dd = k.scan_coefficients()
+            rows = [np.stack([ar, np.zeros_like(ar), cr, np.zeros_like(cr)], axis=1),
+                    np.stack([ac, bc, cc, dc], axis=1)]
+            coef.append(np.concatenate(rows, axis=0))
+            bar, bcr, bac, bbc, bcc, bdc = k.base_coefficients()
+            base.append(np.concatenate([
+                np.stack([bar, np.zeros_like(bar), bcr, np.zeros_like(bcr)], axis=1),
+                np.stack([bac, bbc, bcc, bdc], axis=1)], axis=0))
+            j_off.append(j_off[-1] + len(ar) + len(ac))
+            ddiag.append(dd)
+            delta.append(k.exposure)
+        self.B = len(kernels)
+        self.coef = np.ascontiguousarray(np.concatenate(coef, axis=0) if coef else np.empty((0, 4)))
+        self.base = np.ascontiguousarray(np.concatenate(base, axis=0) if base else np.empty((0, 4)))
+        self.j_off = np.asarray(j_off, dtype=np.int64)
+        self.ddiag = np.asarray(ddiag, dtype=np.float64)
+        self.delta = np.asarray(delta, dtype=np.float64)
+        if self.B and int(np.max(np.diff(self.j_off))) * 2 > GF_MAX_J:
+            raise ValueError(f"kernel state wider than GF_MAX_J = {GF_MAX_J}")
+
+    @property
+    def J(self):
+        return 2 * np.diff(self.j_off)
+
+    def take(self, idx):
+        """Sub-batch (used to shard across ranks)."""
+        out = object.__new__(KernelBatch)
+        idx = np.asarray(idx, dtype=np.int64)
+        widths = np.diff(self.j_off)[idx]
+        rows = np.concatenate([np.arange(self.j_off[i], self.j_off[i + 1]) for i in idx]) \
+            if len(idx) else np.empty(0, dtype=np.int64)
+        out.B = len(idx)
+        out.coef = np.ascontiguousarray(self.coef[rows])
+        out.base = np.ascontiguousarray(self.base[rows])
+        out.j_off = np.concatenate([[0], np.cumsum(widths)]).astype(np.int64)
+        out.ddiag = self.ddiag[idx].copy()
+        out.delta = self.delta[idx].copy()
+        return out
+
+
+class Geometry:
+    """CSR description of a batch of light curves: n_off[B+1], t_off[B]."""
+
+    def __init__(self, n_off, t_off, t_len):
+        self.n_off = np.ascontiguousarray(n_off, dtype=np.int64)
+        self.t_off = np.ascontiguousarray(t_off, dtype=np.int64)
+        self.t_len = int(t_len)
+        self.B = len(self.t_off)
+
+    @classmethod
+    def shared_t(cls, B, N):
+        """B sequences on one common time grid of N points."""
+        return cls(np.arange(B + 1, dtype=np.int64) * N, np.zeros(B, dtype=np.int64), N)
+
+    @classmethod
+    def ragged(cls, lengths):
+        """Each sequence has its own time stamps, concatenated."""
+        off = np.concatenate([[0], np.cumsum(lengths)]).astype(np.int64)
+        return cls(off, off[:-1].copy(), int(off[-1]))
+
+
+class Solver:
+    """One library handle (one CUDA stream) on one device."""
+
+    def __init__(self, device=0):
+        self._lib = load_library()
+        h = ctypes.c_void_p()
+        rc = self._lib.gf_create(int(device), ctypes.byref(h))
+        if rc != 0:
+            raise SolverUnavailable(
+                f"gf_create(device={device}) failed with code {rc}: no usable CUDA device. "
+                f"gadfly_b200 has no CPU fallback.")
+        self._h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.gf_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- bookkeeping -------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != 0:
+            msg = self._lib.gf_last_error(self._h)
+            msg = msg.decode() if msg else ""
+            if rc < 0:
+                raise ValueError(f"gadfly_b200: argument error {rc}: {msg}")
+            raise RuntimeError(f"gadfly_b200: CUDA error {rc}: {msg}")
+
+    def synchronize(self):
+        self._check(self._lib.gf_synchronize(self._h))
+
+    @property
+    def stream(self):
+        return self._lib.gf_stream(self._h)
+
+    @property
+    def launch_count(self):
+        return int(self._lib.gf_launch_count(self._h))
+
+    @property
+    def last_kernel_ms(self):
+        return float(self._lib.gf_last_kernel_ms(self._h))
+
+    def device_info(self, measure=False):
+        sm = ctypes.c_int()
+        fl = ctypes.c_double()
+        self._check(self._lib.gf_device_info(self._h, ctypes.byref(sm), ctypes.byref(fl), int(measure)))
+        return dict(sm_count=sm.value, fp64_flops=fl.value)
+
+    # -- K1 ----------------------------------------------------------------------------
+    def loglike(self, kb, geom, t, y, diag=None, logdet=None, quad=None, status=None, flags=0):
+        """-> (logdet[B], quad[B], status[B]); log L = -(quad + logdet + N log 2 pi)/2."""
+        B = geom.B
+        assert kb.B == B
+        total = int(geom.n_off[-1])
+        keep = []
+        pt, k = _addr(t, count=geom.t_len, name="t"); keep.append(k)
+        py, k = _addr(y, count=total, name="y"); keep.append(k)
+        pd, k = _addr(diag, count=total, name="diag"); keep.append(k)
+        logdet, pl = _out(logdet, (B,))
+        quad, pq = _out(quad, (B,))
+        status, ps = _out(status, (B,), np.int32)
+        n_off, pn = _i64(geom.n_off)
+        t_off, pto = _i64(geom.t_off)
+        j_off, pj = _i64(kb.j_off)
+        self._check(self._lib.gf_loglike_batched(
+            self._h, B, pn, pto, pj, pt, geom.t_len, py, pd, kb.coef.ctypes.data,
+            kb.ddiag.ctypes.data, pl, pq, ps, flags))
+        return logdet, quad, status
+
+    # -- K2 ----------------------------------------------------------------------------
+    def sample(self, kb, geom, t, diag=None, normals=None, seed=0, seq0=0, out=None, logdet=None,
+               status=None, flags=0):
+        """-> (x[sum N], logdet[B], status[B]) with x = L (sqrt(d) o n)."""
+        B = geom.B
+        assert kb.B == B
+        total = int(geom.n_off[-1])
+        keep = []
+        pt, k = _addr(t, count=geom.t_len, name="t"); keep.append(k)
+        pd, k = _addr(diag, count=total, name="diag"); keep.append(k)
+        pn_, k = _addr(normals, count=total, name="normals"); keep.append(k)
+        out, po = _out(out, (total,))
+        logdet, pl = _out(logdet, (B,))
+        status, ps = _out(status, (B,), np.int32)
+        n_off, pn = _i64(geom.n_off)
+        t_off, pto = _i64(geom.t_off)
+        j_off, pj = _i64(kb.j_off)
+        self._check(self._lib.gf_sample_batched(
+            self._h, B, pn, pto, pj, pt, geom.t_len, pd, kb.coef.ctypes.data,
+            kb.ddiag.ctypes.data, pn_, int(seed), int(seq0), po, pl, ps, flags))
+        return out, logdet, status
+
+    # -- K3 ----------------------------------------------------------------------------
+    def factor(self, kb, geom, t, diag=None, d=None, W=None, w_off=None, want_W=True, logdet=None,
+               status=None, flags=0):
+        """-> (d[sum N], W[sum N*J] or None, w_off, logdet[B], status[B])."""
+        B = geom.B
+        assert kb.B == B
+        total = int(geom.n_off[-1])
+        lengths = np.diff(geom.n_off)
+        if w_off is None:
+            w_off = np.concatenate([[0], np.cumsum(lengths * kb.J)]).astype(np.int64)
+            w_total = int(w_off[-1])
+            w_off = w_off[:-1]
+        else:
+            w_off = np.ascontiguousarray(w_off, dtype=np.int64)
+            w_total = int(np.max(w_off + lengths * kb.J)) if B else 0
+        keep = []
+        pt, k = _addr(t, count=geom.t_len, name="t"); keep.append(k)
+        pd, k = _addr(diag, count=total, name="diag"); keep.append(k)
+        d, pdd = _out(d, (total,))
+        if want_W or W is not None:
+            W, pW = _out(W, (w_total,))
+        else:
+            pW = None
+        logdet, pl = _out(logdet, (B,))
+        status, ps = _out(status, (B,), np.int32)
+        n_off, pn = _i64(geom.n_off)
+        t_off, pto = _i64(geom.t_off)
+        j_off, pj = _i64(kb.j_off)
+        w_off_arr, pw = _i64(w_off)
+        self._check(self._lib.gf_factor_batched(
+            self._h, B, pn, pto, pj, pw, pt, geom.t_len, pd, kb.coef.ctypes.data,
+            kb.ddiag.ctypes.data, pdd, pW, pl, ps, flags))
+        return d, W, w_off_arr, logdet, status
+
+    # -- K4 ----------------------------------------------------------------------------
+    def sweep(self, op, kb, geom, w_off, t, W, Y, Z=None, flags=0):
+        """op 0 solve_lower, 1 matmul_lower, 2 solve_upper, 3 matmul_upper; -> Z[sum N]."""
+        B = geom.B
+        assert kb.B == B
+        total = int(geom.n_off[-1])
+        keep = []
+        pt, k = _addr(t, count=geom.t_len, name="t"); keep.append(k)
+        pW, k = _addr(W, name="W"); keep.append(k)
+        pY, k = _addr(Y, count=total, name="Y"); keep.append(k)
+        Z, pZ = _out(Z, (total,))
+        n_off, pn = _i64(geom.n_off)
+        t_off, pto = _i64(geom.t_off)
+        j_off, pj = _i64(kb.j_off)
+        w_off, pw = _i64(w_off)
+        self._check(self._lib.gf_sweep_batched(
+            self._h, int(op), B, pn, pto, pj, pw, pt, geom.t_len, kb.coef.ctypes.data, pW, pY, pZ,
+            flags))
+        return Z
+
+    # -- K5 ----------------------------------------------------------------------------
+    def psd(self, kb, omega, out=None, n_omega=None, flags=0):
+        """-> psd[B, F] of the (exposure-integrated) kernels at angular frequencies omega."""
+        F = int(n_omega) if n_omega is not None else int(np.size(omega))
+        pw, keep = _addr(omega, count=F, name="omega")
+        out, po = _out(out, (kb.B, F))
+        j_off, pj = _i64(kb.j_off)
+        self._check(self._lib.gf_psd_batched(
+            self._h, kb.B, pj, kb.base.ctypes.data, kb.delta.ctypes.data, pw, F, po, flags))
+        return out
+
+
+_default = {}
+_default_lock = threading.Lock()
+
+
+def default_solver(device=None):
+    """Process-wide solver for ``device`` (default: $LOCAL_RANK or 0)."""
+    if device is None:
+        device = int(os.environ.get("GADFLY_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    with _default_lock:
+        if device not in _default:
+            _default[device] = Solver(device)
+        return _default[device]
+
+
+def psd(kernels, omega):
+    """PSD of each kernel on the shared grid ``omega`` (used by ``Term.get_psd``)."""
+    kb = KernelBatch(kernels)
+    return default_solver().psd(kb, np.ascontiguousarray(omega, dtype=np.float64))

@@ -1,0 +1,266 @@
+"""GPU parity tests: every kernel of the hot path, called through the C ABI
+(``libgadfly_b200.so`` via ctypes), against the CPU oracle on the same inputs and against the
+committed golden vectors.  Tolerances are the north star's: log-likelihood and samples rtol 1e-9
+(identical normal draws), PSD rtol 1e-12."""
+import numpy as np
+import pytest
+
+import gadfly_b200 as g
+from gadfly_b200 import batch, philox, solver as S
+from gadfly_b200.solver import Geometry, KernelBatch
+import oracle
+from oracle import terms_oracle as T
+from conftest import golden
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+CASES = ["sun_n384", "sun_ragged", "giant_n512", "gran_only"]
+
+
+def _kernel_from_golden(gd):
+    terms = [g.SHOTerm(S0=r[0], w0=r[1], Q=r[2]) for r in gd["sho"]]
+    delta = float(gd["delta"])
+    if delta > 0:
+        return g.StellarOscillatorKernel(terms=terms, delta=delta)
+    return g.TermSum(*terms)
+
+
+def _maxrel(a, b):
+    return np.max(np.abs(np.asarray(a) - np.asarray(b))) / np.max(np.abs(b))
+
+
+@pytest.mark.parametrize("flags", [0, S.FLAG_REFERENCE_ORDER], ids=["fast", "reforder"])
+@pytest.mark.parametrize("name", CASES)
+def test_loglike_and_sample_vs_golden_and_oracle(solver, name, flags):
+    gd = golden(f"dense_{name}.npz")
+    k = _kernel_from_golden(gd)
+    kb = KernelBatch([k])
+    N = len(gd["t"])
+    geom = Geometry.shared_t(1, N)
+    logdet, quad, status = solver.loglike(kb, geom, gd["t"], gd["y"], gd["diag"], flags=flags)
+    assert status[0] == 0
+    ll = -0.5 * (quad[0] + logdet[0] + N * np.log(2 * np.pi))
+    # dense Cholesky golden
+    assert ll == pytest.approx(float(gd["loglike"]), rel=RTOL)
+    assert logdet[0] == pytest.approx(float(gd["logdet"]), rel=RTOL)
+    # oracle on the same inputs
+    o_logdet, o_quad, o_status = oracle.stream(0, k.scan_coefficients(), gd["t"], gd["y"], diag=gd["diag"])
+    assert logdet[0] == pytest.approx(o_logdet, rel=1e-11)
+    assert quad[0] == pytest.approx(o_quad, rel=RTOL)
+    x, ld2, status = solver.sample(kb, geom, gd["t"], gd["diag"], normals=gd["normals"], flags=flags)
+    assert status[0] == 0 and ld2[0] == pytest.approx(o_logdet, rel=1e-11)
+    o_x = oracle.stream(1, k.scan_coefficients(), gd["t"], gd["normals"], diag=gd["diag"])[0]
+    assert _maxrel(x, o_x) <= RTOL
+    assert _maxrel(x, gd["dot_tril"]) <= 5e-9      # dense Cholesky itself is ~cond*eps accurate
+
+
+@pytest.mark.parametrize("flags", [0, S.FLAG_REFERENCE_ORDER], ids=["fast", "reforder"])
+def test_batched_mixed_widths_shared_and_ragged(solver, solar_kernel, giant_kernel, flags):
+    """Ragged batch: different kernels (J = 172, 124, 10, 2), different lengths incl. N = 1
+    and an empty sequence, own time stamps per sequence."""
+    rng = np.random.default_rng(5)
+    gran = g.StellarOscillatorKernel(terms=list(solar_kernel.term.terms[:5]), delta=6e-5)
+    one = g.SHOTerm(S0=3.0, w0=40.0, Q=2.5)
+    kernels = [solar_kernel, giant_kernel, gran, one, solar_kernel, giant_kernel]
+    lengths = [300, 257, 1000, 64, 1, 0]
+    ts = [np.sort(rng.uniform(0, n * 9e-5, n)) for n in lengths]
+    ts = [np.cumsum(np.maximum(np.diff(t, prepend=0.0), 6.1e-5)) for t in ts]
+    ys = [rng.standard_normal(n) * 50 for n in lengths]
+    diags = [np.full(n, 0.5 + b) for b, n in enumerate(lengths)]
+    t, y, dg = map(np.concatenate, (ts, ys, diags))
+    ll, logdet, quad, status = batch.log_likelihood(kernels, t, y, dg, lengths=lengths, solver=solver,
+                                                    return_parts=True, flags=flags)
+    assert status.tolist() == [0] * 6
+    for b, k in enumerate(kernels):
+        if lengths[b] == 0:
+            assert logdet[b] == 0 and quad[b] == 0
+            continue
+        o_logdet, o_quad, _ = oracle.stream(0, k.scan_coefficients(), ts[b], ys[b], diag=diags[b])
+        assert logdet[b] == pytest.approx(o_logdet, rel=1e-11), b
+        assert quad[b] == pytest.approx(o_quad, rel=RTOL), b
+    nrm = rng.standard_normal(len(t))
+    rows, status = batch.sample(kernels, t, dg, lengths=lengths, normals=nrm, solver=solver,
+                                subtract_mean=False, flags=flags)
+    off = np.concatenate([[0], np.cumsum(lengths)])
+    for b, k in enumerate(kernels):
+        if lengths[b] == 0:
+            continue
+        o_x = oracle.stream(1, k.scan_coefficients(), ts[b], nrm[off[b]:off[b + 1]], diag=diags[b])[0]
+        assert _maxrel(rows[b], o_x) <= RTOL, b
+
+
+def test_many_sequences_more_than_sms(solver, giant_kernel):
+    """More sequences than SMs, shared time grid: the work queue path."""
+    B, N = 333, 96
+    rng = np.random.default_rng(8)
+    t = np.arange(N) * 1.2e-4
+    y = rng.standard_normal((B, N)) * 1e3
+    ll = batch.log_likelihood([giant_kernel] * B, t, y, solver=solver)
+    scan = giant_kernel.scan_coefficients()
+    for b in [0, 1, 147, 148, 200, 332]:
+        ld, q, st = oracle.stream(0, scan, t, y[b])
+        assert ll[b] == pytest.approx(oracle.log_likelihood_from_stream(ld, q, N), rel=RTOL)
+
+
+def test_fused_philox_sampling_matches_host_stream(solver, solar_kernel):
+    B, N = 3, 700
+    t = np.arange(N) * 6e-5
+    x, status = batch.sample([solar_kernel] * B, t, seed=1234, seq0=10, solver=solver, subtract_mean=False)
+    scan = solar_kernel.scan_coefficients()
+    for b in range(B):
+        n = philox.normals(1234, 10 + b, N)
+        ref = oracle.stream(1, scan, t, n)[0]
+        assert _maxrel(x[b], ref) <= RTOL
+    # different sequences / seeds give different draws
+    assert _maxrel(x[0], x[1]) > 0.1
+    x2, _ = batch.sample([solar_kernel], t, seed=1235, seq0=10, solver=solver, subtract_mean=False)
+    assert _maxrel(x2[0], x[0]) > 0.1
+
+
+def test_non_positive_definite_status(solver):
+    k = g.SHOTerm(S0=1.0, w0=2.0, Q=3.0)
+    t = np.array([0.0, 0.0, 1.0, 2.0])
+    ll, logdet, quad, status = batch.log_likelihood([k, k], np.concatenate([t, t + 0.0]),
+                                                    np.ones(8), np.concatenate([np.zeros(4), np.ones(4)]),
+                                                    lengths=[4, 4], solver=solver, return_parts=True)
+    assert status[0] == 2 and status[1] == 0
+    assert ll[0] == -np.inf and np.isfinite(ll[1])
+    with pytest.raises(g.LinAlgError):
+        batch.log_likelihood([k], t, np.ones(4), solver=solver, quiet=False)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_factor_and_sweeps_vs_oracle(solver, name):
+    gd = golden(f"dense_{name}.npz")
+    k = _kernel_from_golden(gd)
+    kb = KernelBatch([k])
+    N = len(gd["t"])
+    geom = Geometry.shared_t(1, N)
+    d, W, w_off, logdet, status = solver.factor(kb, geom, gd["t"], gd["diag"])
+    ogp = oracle.OracleGP(k.scan_coefficients(), gd["t"], diag=gd["diag"])
+    assert status[0] == 0
+    np.testing.assert_allclose(d, ogp.d, rtol=RTOL)
+    assert _maxrel(W.reshape(N, -1), ogp.W) <= RTOL
+    rng = np.random.default_rng(2)
+    Y = rng.standard_normal(N)
+    for op, fn in enumerate([oracle.solve_lower, oracle.matmul_lower, oracle.solve_upper, oracle.matmul_upper]):
+        Z = solver.sweep(op, kb, geom, w_off, gd["t"], W, Y)
+        ref = fn(ogp.t, ogp.c, ogp.U, ogp.W, Y)
+        assert _maxrel(Z, ref) <= RTOL, op
+
+
+def test_gaussian_process_api_vs_golden(solver, solar_kernel):
+    """The celerite2-style calls the tutorials make (reference docs/gadfly/start.rst:30-70)."""
+    gd = golden("dense_sun_n384.npz")
+    gp = g.GaussianProcess(solar_kernel, t=gd["t"], diag=gd["diag"], solver=solver)
+    assert gp.log_likelihood(gd["y"]) == pytest.approx(float(gd["loglike"]), rel=RTOL)
+    assert _maxrel(gp.dot_tril(gd["normals"]), gd["dot_tril"]) <= 5e-9
+    assert _maxrel(gp.apply_inverse(gd["y"]), gd["apply_inverse"]) <= 1e-6
+    Y2 = np.stack([gd["normals"], gd["y"]], axis=1)
+    out = gp.dot_tril(Y2)
+    assert out.shape == Y2.shape and _maxrel(out[:, 0], gd["dot_tril"]) <= 5e-9
+    # sample(): numpy's global generator, as celerite2 draws it; mean subtracted (gadfly/gp.py:392)
+    np.random.seed(42)
+    x = gp.sample()
+    np.random.seed(42)
+    n = np.random.randn(len(gd["t"]))
+    ref = oracle.OracleGP(solar_kernel.scan_coefficients(), gd["t"], diag=gd["diag"]).sample_from_normals(n)
+    assert _maxrel(x, ref) <= RTOL and abs(x.mean()) < 1e-9 * np.abs(x).max()
+    xs = gp.sample(size=3)
+    assert xs.shape == (3, len(gd["t"]))
+    q = gp.sample(return_quantity=True)
+    assert q.unit == g.units.ppm
+    # units at the boundary (reference gadfly/gp.py:61-126)
+    t_days = gd["t"] / 0.0864 * g.units.d
+    gp2 = g.GaussianProcess(solar_kernel, t=t_days, diag=gd["diag"], solver=solver)
+    assert gp2.log_likelihood(gd["y"] * g.units.ppm) == pytest.approx(float(gd["loglike"]), rel=1e-7)
+    with pytest.raises(ValueError):
+        gp.log_likelihood(gd["y"][:-1])
+    with pytest.raises(ValueError):
+        gp.compute(gd["t"], yerr=np.ones(len(gd["t"])), diag=gd["diag"])
+    pred = gp.predict(gd["y"])
+    assert pred.shape == gd["y"].shape
+
+
+def test_gp_not_positive_definite_raises_or_quiet(solver):
+    k = g.SHOTerm(S0=1.0, w0=2.0, Q=3.0)
+    t = np.array([0.0, 0.0, 1.0])
+    with pytest.raises(g.LinAlgError):
+        g.GaussianProcess(k, t=t, solver=solver)
+    gp = g.GaussianProcess(k, solver=solver)
+    gp.compute(t, quiet=True)
+    assert gp.log_likelihood(np.ones(3)) == -np.inf
+
+
+def test_psd_vs_oracle_and_reference_closed_form(solver, solar_kernel, giant_kernel):
+    gd = golden("ref_sho_psd.npz")
+    ref_kernel = g.TermSum(*[g.SHOTerm(S0=r[0], w0=r[1], Q=r[2]) for r in gd["params"]])
+    got = ref_kernel.get_psd(gd["omega"])
+    np.testing.assert_allclose(got, oracle.psd(ref_kernel.base_coefficients(), gd["omega"]), rtol=1e-12)
+    far = gd["omega"] < 2 * np.pi * 800.0
+    np.testing.assert_allclose(got[far], gd["psd_sum"][far], rtol=1e-12)   # reference _sho_psd
+    np.testing.assert_allclose(got, gd["psd_sum"], rtol=1e-8)
+    # exposure-integrated kernels, batched, dense grid incl. omega = 0
+    omega = 2 * np.pi * np.concatenate([[0.0], np.linspace(0.01, 8333.0, 20001)])
+    kb = KernelBatch([solar_kernel, giant_kernel])
+    out = solver.psd(kb, omega)
+    for b, k in enumerate([solar_kernel, giant_kernel]):
+        np.testing.assert_allclose(out[b], oracle.psd(k.base_coefficients(), omega, k.delta), rtol=1e-12)
+    assert out.shape == (2, len(omega))
+    np.testing.assert_allclose(g.kernel_psd(solar_kernel, omega / (2 * np.pi), solver=solver), out[0], rtol=0)
+
+
+def test_device_pointers_and_async(solver, solar_kernel):
+    """Inputs and outputs already resident in HBM (torch tensors) give the same numbers."""
+    import torch
+    B, N = 4, 256
+    rng = np.random.default_rng(3)
+    t = np.arange(N) * 6e-5
+    y = rng.standard_normal((B, N)) * 300
+    kb = KernelBatch([solar_kernel] * B)
+    geom = Geometry.shared_t(B, N)
+    ref = solver.loglike(kb, geom, t, y)
+    dev = torch.device('cuda', solver.device)
+    td, yd = torch.from_numpy(t).to(dev), torch.from_numpy(y).to(dev)
+    ld = torch.empty(B, dtype=torch.float64, device=dev)
+    qd = torch.empty(B, dtype=torch.float64, device=dev)
+    sd = torch.empty(B, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    solver.loglike(kb, geom, td, yd, logdet=ld, quad=qd, status=sd, flags=S.FLAG_ASYNC)
+    solver.synchronize()
+    np.testing.assert_array_equal(ld.cpu().numpy(), ref[0])
+    np.testing.assert_array_equal(qd.cpu().numpy(), ref[1])
+    assert solver.last_kernel_ms > 0 and solver.launch_count > 0
+
+
+def test_round_trip_sample_psd_statistics(solver, solar_kernel):
+    """The reference's only hot-path test (gadfly/tests/test_core.py:17-49): samples drawn from
+    the kernel have the kernel's power spectrum (binned FFT PSD within 5 sigma, 3-1000 uHz)."""
+    np.random.seed(42)
+    N = 100_000
+    t_days = np.linspace(0, 100, N)
+    gp = g.GaussianProcess(solar_kernel, t=t_days * g.units.d, solver=solver)
+    for _ in range(3):
+        flux = gp.sample()
+        ps = g.PowerSpectrum.from_light_curve(t_days, flux).bin(15)
+        model = solar_kernel.get_psd(2 * np.pi * ps.frequency)
+        ok = (ps.frequency < 1e3) & (ps.frequency > 3)
+        dev = np.abs((model[ok] - ps.power[ok]) / np.nanmax(ps.error))
+        assert np.nanmax(dev) < 5
+
+
+def test_large_property_checks(solver, solar_kernel):
+    """Size-independent properties at a size the oracle does not finish quickly:
+    L^-1 (L n) = n through the fused sample + loglike kernels, and log-det additivity of a
+    shared factor across replicas."""
+    N, B = 20000, 4
+    t = np.arange(N) * 6e-5
+    x, status = batch.sample([solar_kernel] * B, t, seed=99, solver=solver, subtract_mean=False)
+    assert status.tolist() == [0] * B
+    ll, logdet, quad, status = batch.log_likelihood([solar_kernel] * B, t, x, solver=solver, return_parts=True)
+    # quad = |L^-1 x|^2_D^-1 = sum n^2  for x = L sqrt(D) n
+    for b in range(B):
+        n = philox.normals(99, b, N)
+        assert quad[b] == pytest.approx(np.sum(n * n), rel=1e-8)
+    assert np.ptp(logdet) <= 1e-12 * abs(logdet[0])
