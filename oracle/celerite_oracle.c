@@ -223,22 +223,21 @@ long orc_stream(int mode, long N, int Jr, int Jc, const double *t, const double 
     for (long n = 1; n < N; ++n) {
         double dt = t[n - 1] - t[n];
         for (int j = 0; j < J; ++j) p[j] = exp(c[j] * dt);
-        for (int j = 0; j < J; ++j) {
-            double dw = dprev * w[j];
-            double *Sj = S + (size_t)j * J;
-            for (int k = 0; k < J; ++k) Sj[k] += dw * w[k];
-        }
-        for (int j = 0; j < J; ++j) {
-            double *Sj = S + (size_t)j * J;
-            for (int k = 0; k < J; ++k) Sj[k] = (p[j] * Sj[k]) * p[k];
-        }
         for (int j = 0; j < J; ++j) F[j] = p[j] * (F[j] + w[j] * zprev);
         fill_row(Jr, Jc, t[n], ar, ac, bc, dc, u, v);
         for (int k = 0; k < J; ++k) tmp[k] = 0.0;
+        /* one pass over S: rank-1 update, decay, and tmp = u S -- per element the same
+         * operations in the same order as orc_factor's three passes (bit-identical results
+         * in the non-contracting build), but S streams through the cache once per step */
         for (int j = 0; j < J; ++j) {
-            const double *Sj = S + (size_t)j * J;
-            double uj = u[j];
-            for (int k = 0; k < J; ++k) tmp[k] += uj * Sj[k];
+            const double dw = dprev * w[j], pj = p[j], uj = u[j];
+            double *restrict Sj = S + (size_t)j * J;
+            for (int k = 0; k < J; ++k) {
+                double sjk = Sj[k] + dw * w[k];
+                sjk = (pj * sjk) * p[k];
+                Sj[k] = sjk;
+                tmp[k] += uj * sjk;
+            }
         }
         double dn = ((diag ? diag[n] : 0.0) + ddiag) + sa;
         double acc = 0.0;
