@@ -1,20 +1,24 @@
 // Fast semiseparable scan (K1 log-likelihood, K2 sample, K3 factor) for sm_100a, FP64.
 //
 // One CTA per sequence (persistent CTAs pull sequences from a queue), 1 CTA per SM, three
-// warpgroups with re-balanced register budgets (setmaxnreg):
+// warpgroups with re-balanced register budgets (setmaxnreg), three roles:
 //
-//   WG0, WG1  "matrix" threads.  The J x J symmetric state lives in REGISTERS: each thread owns
-//             one 8x8 tile of the upper triangle (253 tiles at J = 176).  Per time step and per
-//             stored element: one FMA for the rank-1 update and two FMAs for the two matrix-
-//             vector partial products the symmetric tile contributes to (3 DFMA per element;
-//             the FP64 pipe is the binding resource).  Tiles are grouped 2x2 per 4 lanes so
-//             that half of the partial sums are combined with warp shuffles and the operand
-//             vectors are read as conflict-free / broadcast LDS.128.
-//   WG2       "vector" threads, one lane per complex term (cos and sin columns).  They generate
-//             the rows u_n, v_n on the fly from t (sincos / exp, nothing of size N*J is read),
-//             finish the matrix-vector product, form the pivot d_n, the new row w_n, the
-//             forward-substitution state F and the outputs, and publish the operands of the
-//             next matrix phase.
+//   matrix (WG0, WG1; 8 warps)  The J x J symmetric state lives in REGISTERS: each thread owns
+//       one 8x8 tile of the upper triangle (253 tiles at J = 176).  Per time step and stored
+//       element: one FMA for the rank-1 update and two FMAs for the two matrix-vector partial
+//       products a symmetric tile contributes to -- 3 DFMA per element; the FP64 pipe is the
+//       binding resource.  Tiles are grouped 2x2 per 4 lanes so that half of the partial sums
+//       are combined by warp shuffles and the operand vectors are read as conflict-free /
+//       broadcast LDS.128.  The matrix warps also reduce the quadratic form u~ S~ u~^T, so the
+//       pivot needs no reduction on the vector side.
+//   chain (WG2 warps 0-2)  one lane per complex term (cos + sin column): finishes the
+//       matrix-vector product from the partial sums, forms the pivot d_n, the new row w~_n, the
+//       forward-substitution state, the outputs, and publishes the operands of matrix phase n+2.
+//   producer (WG2 warp 3)  generates the rows u~_n, v~_n on the fly from t (nothing of size N*J
+//       is read): Cody-Waite sincos of the exactly rounded phase d*t_n, decay factors by a
+//       product recurrence with a first-order correction for cadence jitter (exp only when the
+//       cadence changes), Philox normals for sampling; hands rows over through a shared-memory
+//       ring, half a ring at a time.
 //
 // Two algebraic rearrangements of the celerite recurrences make this fast;
 // both are exact in exact arithmetic and differ from the reference order only in rounding:
@@ -26,10 +30,11 @@
 //      every RENORM_STEPS steps or when c_max (t_n - t_ref) would exceed RENORM_LIMIT, so all
 //      scaled quantities stay far inside the FP64 range; large gaps just drive r -> 0.
 //  (2) One-step-stale matrix-vector product.  h_n = u~_n S~(n) is evaluated as
-//      g_n + d_{n-1} (u~_n . w~_{n-1}) w~_{n-1} with g_n = u~_n S~(n-1), so matrix phase n needs
-//      only w~_{n-2}: the vector work of step n-1 overlaps matrix phase n instead of
-//      serialising with it.  Synchronisation is by named barriers (producer bar.arrive,
-//      consumer bar.sync), double-buffered operands and partial sums.
+//      g_n + d_{n-1} alpha_n w~_{n-1} with g_n = u~_n S~(n-1) and alpha_n = u~_n . w~_{n-1}, so
+//      matrix phase n needs only w~_{n-2}: the chain work of step n-1 overlaps matrix phase n
+//      instead of serialising with it.  Likewise d_n = a_n - (u~_n S~(n-1) u~_n^T + d_{n-1}
+//      alpha_n^2).  Synchronisation is by named barriers (producer bar.arrive, consumer
+//      bar.sync) over double-buffered operands and partial sums.
 #include "common.cuh"
 
 namespace gf {
@@ -38,30 +43,46 @@ namespace {
 
 constexpr int FT_THREADS = 384;
 constexpr int MAT_THREADS = 256;
-constexpr int HLP_THREADS = 128;
-constexpr int HLP_WARPS = 4;
-constexpr int TPW = 22;              // complex terms per vector warp (4 x 22 = 88 >= JP_MAX / 2)
+constexpr int MAT_WARPS = 8;
+constexpr int CH_THREADS = 96;
+constexpr int TPW = 30;              // complex terms per chain warp (3 x 30 = 90 >= 88)
+constexpr int JC_MAX = JP_MAX / 2;   // 88
 constexpr int NSB_MAX = NB_MAX / 2;  // 16 x 16 super-blocks per side
 constexpr int NSLOT = NSB_MAX + 1;   // partial-sum slots per column
-constexpr int RING = 64;             // staged t / y / diag entries
-constexpr int CHUNK = 32;
+constexpr int RR = 16;               // row ring depth (two halves)
+constexpr int HALF = 8;
 constexpr int REG_MAT = 208;
 constexpr int REG_HLP = 88;
 constexpr double RENORM_LIMIT = 64.0;
 constexpr int RENORM_STEPS = 64;
 
-constexpr int BAR_OPS = 1;    // ids 1, 2: operands of matrix phase (n & 1) are ready
-constexpr int BAR_PART = 3;   // ids 3, 4: partial sums of matrix phase (n & 1) are ready
-constexpr int BAR_HLP = 5;    // vector-warp internal
+// named barriers (0 is __syncthreads)
+constexpr int BAR_OPS = 1;     // 1, 2: operands of matrix phase (n & 1) ready   [chain -> matrix]
+constexpr int BAR_PART = 3;    // 3, 4: partial sums of matrix phase ready       [matrix -> chain]
+constexpr int BAR_CH = 5;      // chain-warp internal
+constexpr int BAR_FULL = 6;    // 6, 7: ring half produced                       [producer -> chain]
+constexpr int BAR_EMPTY = 8;   // 8, 9: ring half consumed                       [chain -> producer]
+constexpr int N_OPS = CH_THREADS + MAT_THREADS;
+constexpr int N_RING = CH_THREADS + 32;
 
 struct FastSmem {
     double2 A[2][TILE][NB_MAX];     // (u~_n[k], d w~[k]) for k = 8 b + e, indexed [e][b]
     double2 C[2][TILE][NB_MAX];     // (u~_n[k], w~[k])
     double R[2][JP_MAX];            // renormalisation factors r[k] of the phase
     double P[2][NSLOT][JP_MAX];     // partial sums of g_n, natural column order
-    double2 red2[2][HLP_WARPS];     // (beta, gamma) per vector warp
-    double red1[2][HLP_WARPS];      // alpha per vector warp
-    double tbuf[RING], ybuf[RING], dbuf[RING];
+    double QF[2][MAT_WARPS];        // partial sums of u~ S~ u~^T per matrix warp
+    double2 red2[2][4];             // (alpha, gamma) per chain warp
+    // row ring, written by the producer warp
+    double2 RU[RR][JC_MAX];         // (u~ cos column, u~ sin column) per term
+    double2 RV[RR][JC_MAX];         // (v~ cos column, v~ sin column)
+    double Rr[RR][JC_MAX];          // frame change factor into this step's frame (1 if none)
+    double Rq[RR][JC_MAX];          // q of this step (factor mode: W is stored unscaled)
+    double Ra[RR];                  // a_n = (diag_n + ddiag) + sum a'
+    double Ry[RR];                  // y_n, or the normal draw n_n
+    int Rflag[RR];                  // this step renormalises
+    double2 Kab[JC_MAX + 8];        // per-term (a', b')
+    double2 Kcd[JC_MAX + 8];        // per-term (c, d)
+    double2 Kp[JC_MAX + 8];         // per-term cached decay over the cadence dt0: (p0, 1 / p0)
     int renorm[2];
     long long stop;                 // first matrix phase that must not run
     int next;
@@ -81,48 +102,35 @@ __device__ __forceinline__ double shfl_xor_d(double x, int m)
     return __shfl_xor_sync(0xffffffffu, x, m);
 }
 
-struct Row {
-    double uc, us, vc, vs;   // u~, v~ of the cos and sin column
-    double r;                // frame change factor into this step's frame (1 if none)
-    double q;                // exp(-c (t - t_ref)) of this step (1 on a renormalising step)
-    int flag;                // this step renormalises
-};
-
-struct RowGen {
-    double ca, cb, cc, cd;   // a', b', c, d of this lane's term
-    double cmax;             // largest c of the sequence
-    double t_ref;
-    long long m_ref;
-
-    __device__ __forceinline__ Row make(double tm, long long m, bool valid)
-    {
-        Row row;
-        row.uc = row.us = row.vc = row.vs = 0.0;
-        row.r = 1.0; row.q = 1.0; row.flag = 0;
-        if (!valid) return row;
-        const double dt = tm - t_ref;
-        const bool rn = (cmax * dt > RENORM_LIMIT) || (m - m_ref >= RENORM_STEPS);
-        const double E = cc * dt;
-        double q = 1.0, qinv = 1.0;
-        if (rn) {
-            row.r = exp(-E);
-            row.flag = 1;
-            t_ref = tm;
-            m_ref = m;
-        } else {
-            q = exp(-E);
-            qinv = exp(E);
-        }
-        row.q = q;
-        double sn, cs;
-        sincos(cd * tm, &sn, &cs);
-        row.uc = (ca * cs + cb * sn) * q;
-        row.us = (ca * sn - cb * cs) * q;
-        row.vc = cs * qinv;
-        row.vs = sn * qinv;
-        return row;
-    }
-};
+// sin and cos of a double that is already the rounded phase d * t: three-constant Cody-Waite
+// reduction with FMA (absolute error of the reduced argument ~2e-16 for |x| < 2^30) and the
+// fdlibm kernel polynomials on [-pi/4, pi/4].  No slow path, no local memory.
+__device__ __forceinline__ void sincos_cw(double x, double *sn, double *cs)
+{
+    if (!(fabs(x) < 1.0e9)) { sincos(x, sn, cs); return; }
+    const double kd = rint(x * 0.6366197723675814);
+    const int q = (int)kd;
+    double r = fma(-kd, 1.5707963267948966, x);
+    r = fma(-kd, 6.123233995736766e-17, r);
+    r = fma(-kd, -1.4973849048591698e-33, r);
+    const double z = r * r;
+    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    ps = fma(ps, z, 2.75573137070700676789e-06);
+    pc = fma(pc, z, -2.75573143513906633035e-07);
+    ps = fma(ps, z, -1.98412698298579493134e-04);
+    pc = fma(pc, z, 2.48015872894767294178e-05);
+    ps = fma(ps, z, 8.33333333332248946124e-03);
+    pc = fma(pc, z, -1.38888888888741095749e-03);
+    ps = fma(ps, z, -1.66666666666666324348e-01);
+    pc = fma(pc, z, 4.16666666666666019037e-02);
+    const double s = fma(ps * z, r, r);
+    const double c = fma(z * z, pc, fma(-0.5, z, 1.0));
+    const double s1 = (q & 1) ? c : s;
+    const double c1 = (q & 1) ? s : c;
+    *sn = (q & 2) ? -s1 : s1;
+    *cs = ((q + 1) & 2) ? -c1 : c1;
+}
 
 // ------------------------------------------------------------------------------------------
 // matrix warpgroups
@@ -164,6 +172,9 @@ __device__ __forceinline__ void matrix_loop(FastSmem &sm, const int mt, const in
 {
     const TileMap tm = make_tile_map(mt, nsb);
     const int bi = tm.bi, bj = tm.bj;
+    // weight of this tile in the quadratic form: off-diagonal tiles stand for their mirror too
+    const double qw = (tm.kind == 3) ? 0.0 : ((bi == bj) ? 1.0 : 2.0);
+    const int lane = mt & 31, warp = mt >> 5;
     double S[TILE][TILE];
 #pragma unroll
     for (int i = 0; i < TILE; ++i)
@@ -172,7 +183,7 @@ __device__ __forceinline__ void matrix_loop(FastSmem &sm, const int mt, const in
 
     for (long long n = 0; n < N; ++n) {
         const int par = (int)(n & 1);
-        bar_sync(BAR_OPS + par, FT_THREADS);
+        bar_sync(BAR_OPS + par, N_OPS);
         if (n >= sm.stop) break;
 
         double uj[TILE], wj[TILE];
@@ -215,6 +226,12 @@ __device__ __forceinline__ void matrix_loop(FastSmem &sm, const int mt, const in
             rowp[i] = rp;
         }
 
+        // quadratic form u~ S~ u~^T: this tile's share, reduced over the warp
+        double qf = 0.0;
+#pragma unroll
+        for (int j = 0; j < TILE; ++j) qf = fma(colp[j], uj[j], qf);
+        qf *= qw;
+
         // 2x2 group: combine the two tiles of a block row (lane ^ 1) and of a block column
         // (lane ^ 2); each lane keeps four of the eight sums
         double rs[4], cs[4];
@@ -227,6 +244,10 @@ __device__ __forceinline__ void matrix_loop(FastSmem &sm, const int mt, const in
             const double keep_c = tm.ri ? colp[4 + q] : colp[q];
             cs[q] = keep_c + shfl_xor_d(send_c, 2);
         }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) qf += shfl_xor_d(qf, off);
+        if (lane == 0) sm.QF[par][warp] = qf;
+
         if (tm.kind == 0) {
             double *pr = &sm.P[par][tm.slot_row][bi * TILE + tm.cj * 4];
             double *pc = &sm.P[par][tm.slot_col][bj * TILE + tm.ri * 4];
@@ -248,211 +269,292 @@ __device__ __forceinline__ void matrix_loop(FastSmem &sm, const int mt, const in
                 *reinterpret_cast<double2 *>(pc + 2 * q) = make_double2(colp[2 * q], colp[2 * q + 1]);
             }
         }
-        bar_arrive(BAR_PART + par, FT_THREADS);
+        bar_arrive(BAR_PART + par, N_OPS);
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// vector warpgroup
+// producer warp: rows of U, V (scaled), a_n, y_n / normal draws -> ring
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void hreduce2(FastSmem &sm, int par, int hw, int lane, double &a, double &b)
-{
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) { a += shfl_xor_d(a, off); b += shfl_xor_d(b, off); }
-    if (lane == 0) sm.red2[par][hw] = make_double2(a, b);
-    bar_sync(BAR_HLP, HLP_THREADS);
-    double sa = 0.0, sb = 0.0;
-#pragma unroll
-    for (int w = 0; w < HLP_WARPS; ++w) { const double2 v = sm.red2[par][w]; sa += v.x; sb += v.y; }
-    a = sa; b = sb;
-}
-
-__device__ __forceinline__ void hreduce1(FastSmem &sm, int par, int hw, int lane, double &a)
-{
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) a += shfl_xor_d(a, off);
-    if (lane == 0) sm.red1[par][hw] = a;
-    bar_sync(BAR_HLP, HLP_THREADS);
-    double sa = 0.0;
-#pragma unroll
-    for (int w = 0; w < HLP_WARPS; ++w) sa += sm.red1[par][w];
-    a = sa;
-}
+__device__ __forceinline__ long long ring_halves(long long N) { return (N + 1) / HALF + 1; }
 
 template <int MODE>
-__device__ __forceinline__ void vector_loop(FastSmem &sm, const ScanArgs &A, const int ht,
-                                            const int b, const int nsb, const long long N,
-                                            const int Jc)
+__device__ __forceinline__ void producer_loop(FastSmem &sm, const ScanArgs &A, const int lane,
+                                              const int b, const long long N, const int Jc)
 {
-    const int hw = ht >> 5, lane = ht & 31;
-    const int term = hw * TPW + lane;
-    const bool act = (lane < TPW) && (term < Jc);
-    const int k0 = 2 * term;                 // cos column; sin column is k0 + 1
-    const int kb = k0 >> 3, ke = k0 & 7;     // both columns sit in block kb (ke is even)
     const long long n0 = A.n_off[b];
     const long long j0 = A.j_off[b];
     const double *t = A.t + A.t_off[b];
     const double *y = A.y ? A.y + n0 : nullptr;
     const double *dg = A.diag ? A.diag + n0 : nullptr;
     const double ddiag = A.ddiag[b];
-    const int J = 2 * Jc;
-    // sampling without external normals: the draws enter through the staging ring like y
     const bool philox = (MODE == MODE_SAMPLE) && (A.y == nullptr);
     const uint64_t seq = A.seq0 + (uint64_t)b;
 
-    RowGen gen;
-    gen.ca = gen.cb = gen.cc = gen.cd = 0.0;
-    if (act) {
-        const double *cf = A.coef + 4 * (j0 + term);
-        gen.ca = cf[0]; gen.cb = cf[1]; gen.cc = cf[2]; gen.cd = cf[3];
-    }
-    // sum of a' in term order; largest decay rate
+    // sum of a' in term order (as the oracle adds it); largest decay rate
     double sum_a = 0.0, cmax = 0.0;
     for (int j = 0; j < Jc; ++j) {
         sum_a += A.coef[4 * (j0 + j)];
         cmax = fmax(cmax, A.coef[4 * (j0 + j) + 2]);
     }
-    gen.cmax = cmax;
+    // this lane's terms: lane, lane + 32, lane + 64; their constants stay in shared memory
+    constexpr int TPL = 3;
+    double q[TPL], qinv[TPL];
+    bool act[TPL];
+#pragma unroll
+    for (int k = 0; k < TPL; ++k) {
+        const int term = lane + 32 * k;
+        act[k] = term < Jc;
+        double4 cf = make_double4(0.0, 0.0, 0.0, 0.0);
+        if (act[k]) cf = *reinterpret_cast<const double4 *>(A.coef + 4 * (j0 + term));
+        sm.Kab[term] = make_double2(cf.x, cf.y);
+        sm.Kcd[term] = make_double2(cf.z, cf.w);
+        sm.Kp[term] = make_double2(1.0, 1.0);
+        q[k] = 1.0; qinv[k] = 1.0;
+    }
+    __syncwarp();
+    double dt0 = 0.0;            // cadence the cached decay factors p0 belong to
+    double t_prev = 0.0, t_ref = 0.0;
+    long long m_ref = 0;
 
-    // stage the first RING entries of t / y / diag
-    {
-        const int role = ht >> 5, l = ht & 31;
-        for (int c = 0; c < RING; c += CHUNK) {
-            const long long m = c + l;
-            if (m < N) {
-                if (role == 0) sm.tbuf[m] = t[m];
-                if (role == 1) sm.ybuf[m] = y ? y[m] : (philox ? philox_normal(A.seed, seq, (uint64_t)m) : 0.0);
-                if (role == 2) sm.dbuf[m] = dg ? dg[m] : 0.0;
+    // per-half input staging: lanes 0-7 t, 8-15 y (or normal), 16-23 diag
+    auto load_half = [&](long long m0) -> double {
+        const int role = lane >> 3;
+        const long long m = m0 + (lane & 7);
+        double v = 0.0;
+        if (m < N) {
+            if (role == 0) v = t[m];
+            else if (role == 1) v = y ? y[m] : (philox ? philox_normal(A.seed, seq, (uint64_t)m) : 0.0);
+            else if (role == 2) v = dg ? dg[m] : 0.0;
+        }
+        return v;
+    };
+
+    const long long nh = ring_halves(N);
+    double pend = load_half(0);
+    for (long long hi = 0; hi < nh; ++hi) {
+        const int h = (int)(hi & 1);
+        const double cur = pend;
+        if (hi + 1 < nh) pend = load_half((hi + 1) * HALF);
+        if (hi >= 2) bar_sync(BAR_EMPTY + h, N_RING);
+        const bool aborted = sm.stop < N;    // the chain gave up: keep only the hand-shake going
+        if (!aborted) {
+#pragma unroll 1
+            for (int s = 0; s < HALF; ++s) {
+                const long long m = hi * HALF + s;
+                const int slot = h * HALF + s;
+                const double tm = __shfl_sync(0xffffffffu, cur, s);
+                const double ym = __shfl_sync(0xffffffffu, cur, 8 + s);
+                const double dm = __shfl_sync(0xffffffffu, cur, 16 + s);
+                const bool valid = m < N;
+                const double dt = (m > 0) ? (tm - t_prev) : 0.0;
+                const bool rn = valid && m > 0 &&
+                                ((cmax * (tm - t_ref) > RENORM_LIMIT) || (m - m_ref >= RENORM_STEPS));
+                // decay over this step: cached factors, corrected to first order for a jittered
+                // cadence (|c eps| < 1e-8 for every term); exp only when the cadence changes
+                const double eps = dt - dt0;
+                const bool use_exp = valid && !(fabs(cmax * eps) < 1e-8);
+#pragma unroll
+                for (int k = 0; k < TPL; ++k) {
+                    double uc = 0.0, us = 0.0, vc = 0.0, vs = 0.0, r = 1.0;
+                    const int term = lane + 32 * k;
+                    if (valid && act[k]) {
+                        const double2 ab = sm.Kab[term], cdk = sm.Kcd[term];
+                        double p, pinv;
+                        if (use_exp) {
+                            p = exp(-cdk.x * dt);
+                            pinv = exp(cdk.x * dt);
+                            sm.Kp[term] = make_double2(p, pinv);
+                        } else {
+                            const double2 pc = sm.Kp[term];
+                            const double ce = cdk.x * eps;
+                            p = fma(-ce, pc.x, pc.x);
+                            pinv = fma(ce, pc.y, pc.y);
+                        }
+                        double qn = q[k] * p, qi = qinv[k] * pinv;
+                        if (rn) { r = qn; qn = 1.0; qi = 1.0; }
+                        q[k] = qn; qinv[k] = qi;
+                        double sn, cs;
+                        sincos_cw(cdk.y * tm, &sn, &cs);
+                        uc = (ab.x * cs + ab.y * sn) * qn;
+                        us = (ab.x * sn - ab.y * cs) * qn;
+                        vc = cs * qi;
+                        vs = sn * qi;
+                    }
+                    if (term < JC_MAX) {
+                        sm.RU[slot][term] = make_double2(uc, us);
+                        sm.RV[slot][term] = make_double2(vc, vs);
+                        sm.Rr[slot][term] = r;
+                        if (MODE == MODE_FACTOR) sm.Rq[slot][term] = q[k];
+                    }
+                }
+                if (use_exp) dt0 = dt;
+                if (rn) { t_ref = tm; m_ref = m; }
+                if (valid) t_prev = tm;
+                if (m == 0) t_ref = tm;
+                if (lane == 0) {
+                    sm.Ra[slot] = (dm + ddiag) + sum_a;
+                    sm.Ry[slot] = ym;
+                    sm.Rflag[slot] = rn ? 1 : 0;
+                }
             }
         }
+        bar_arrive(BAR_FULL + h, N_RING);
     }
-    bar_sync(BAR_HLP, HLP_THREADS);
+}
 
-    gen.t_ref = sm.tbuf[0];
-    gen.m_ref = 0;
-    Row r0 = gen.make(sm.tbuf[0], 0, act);
-    Row r1 = gen.make(N > 1 ? sm.tbuf[1] : 0.0, 1, act && N > 1);
-    Row r2 = gen.make(N > 2 ? sm.tbuf[2] : 0.0, 2, act && N > 2);
-    // the renormalisation decision is uniform, but idle lanes skipped make(): recompute it
-    // for them from lane 0 of the warp (all active lanes agree)
-    r0.flag = __shfl_sync(0xffffffffu, r0.flag, 0);
-    r1.flag = __shfl_sync(0xffffffffu, r1.flag, 0);
-    r2.flag = __shfl_sync(0xffffffffu, r2.flag, 0);
+// ------------------------------------------------------------------------------------------
+// chain warps
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void chain_reduce2(FastSmem &sm, int par, int hw, int lane, double &a, double &b)
+{
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) { a += shfl_xor_d(a, off); b += shfl_xor_d(b, off); }
+    if (lane == 0) sm.red2[par][hw] = make_double2(a, b);
+    bar_sync(BAR_CH, CH_THREADS);
+    const double2 v0 = sm.red2[par][0], v1 = sm.red2[par][1], v2 = sm.red2[par][2];
+    a = (v0.x + v1.x) + v2.x;
+    b = (v0.y + v1.y) + v2.y;
+}
+
+template <int MODE>
+__device__ __forceinline__ void chain_loop(FastSmem &sm, const ScanArgs &A, const int ht,
+                                           const int b, const int nsb, const long long N,
+                                           const int Jc)
+{
+    const int hw = ht >> 5, lane = ht & 31;
+    const int term = hw * TPW + lane;
+    const bool act = (lane < TPW) && (term < Jc);
+    const int tix = act ? term : 0;          // safe index for ring reads
+    const int k0 = 2 * tix;                  // cos column; sin column is k0 + 1
+    const int kb = k0 >> 3, ke = k0 & 7;     // both columns sit in block kb (ke is even)
+    const long long n0 = A.n_off[b];
+    const int J = 2 * Jc;
+    const long long nh = ring_halves(N);
+
+    bar_sync(BAR_FULL + 0, N_RING);          // ring half 0: rows 0..7
 
     // operands of matrix phases 0 and 1: rows 0 / 1, no rank-1 term yet
     if (act) {
-        sm.A[0][ke][kb] = make_double2(r0.uc, 0.0);     sm.C[0][ke][kb] = make_double2(r0.uc, 0.0);
-        sm.A[0][ke + 1][kb] = make_double2(r0.us, 0.0); sm.C[0][ke + 1][kb] = make_double2(r0.us, 0.0);
-        sm.A[1][ke][kb] = make_double2(r1.uc, 0.0);     sm.C[1][ke][kb] = make_double2(r1.uc, 0.0);
-        sm.A[1][ke + 1][kb] = make_double2(r1.us, 0.0); sm.C[1][ke + 1][kb] = make_double2(r1.us, 0.0);
+        const double2 u0 = sm.RU[0][tix], u1 = sm.RU[1][tix];
+        sm.A[0][ke][kb] = make_double2(u0.x, 0.0);     sm.C[0][ke][kb] = make_double2(u0.x, 0.0);
+        sm.A[0][ke + 1][kb] = make_double2(u0.y, 0.0); sm.C[0][ke + 1][kb] = make_double2(u0.y, 0.0);
+        sm.A[1][ke][kb] = make_double2(u1.x, 0.0);     sm.C[1][ke][kb] = make_double2(u1.x, 0.0);
+        sm.A[1][ke + 1][kb] = make_double2(u1.y, 0.0); sm.C[1][ke + 1][kb] = make_double2(u1.y, 0.0);
         sm.R[0][k0] = 1.0; sm.R[0][k0 + 1] = 1.0;
-        sm.R[1][k0] = r1.r; sm.R[1][k0 + 1] = r1.r;
+        const double r1 = sm.Rr[1][tix];
+        sm.R[1][k0] = r1; sm.R[1][k0 + 1] = r1;
     }
-    if (ht == 0) { sm.renorm[0] = 0; sm.renorm[1] = r1.flag; }
-    bar_arrive(BAR_OPS + 0, FT_THREADS);
-    if (N > 1) bar_arrive(BAR_OPS + 1, FT_THREADS);
+    if (ht == 0) { sm.renorm[0] = 0; sm.renorm[1] = (N > 1) ? sm.Rflag[1] : 0; }
+    bar_arrive(BAR_OPS + 0, N_OPS);
+    if (N > 1) bar_arrive(BAR_OPS + 1, N_OPS);
 
     double wc = 0.0, ws = 0.0;       // w~_{n-1}, in the frame of step n
-    double Fc = 0.0, Fs = 0.0;       // F~ of this term
-    double kappa = 0.0;              // d_{n-1} (u~_n . w~_{n-1})
+    double Fc = 0.0, Fs = 0.0;       // F~_n of this term, frame of step n
+    double alpha = 0.0, gamma = 0.0; // u~_n . w~_{n-1},  u~_n . F~_n
+    double dprev = 0.0;
     double logdet = 0.0, prod = 1.0, quad = 0.0;
     int32_t fail = 0;
-    double pend = 0.0;               // staged global load in flight
+    bool drain = false;
 
     for (long long n = 0; n < N; ++n) {
         const int par = (int)(n & 1);
-        // staging of the input ring, one chunk ahead: issue at n % CHUNK == 0, store one step later
-        {
-            const int role = ht >> 5, l = ht & 31;
-            const long long base = (n & ~(long long)(CHUNK - 1)) + CHUNK;
-            const long long m = base + l;
-            const int ph = (int)(n & (CHUNK - 1));
+        const int s0 = (int)(n & (RR - 1)), s1 = (int)((n + 1) & (RR - 1)), s2 = (int)((n + 2) & (RR - 1));
+        // ring hand-over: row n + 2 is first touched here
+        if (((n + 2) & (HALF - 1)) == 0 && (n + 2) / HALF < nh)
+            bar_sync(BAR_FULL + (int)(((n + 2) / HALF) & 1), N_RING);
+
+        if (!drain) {
+            bar_sync(BAR_PART + par, N_OPS);
+            // g_n: sum of the partial products; two independent accumulators per column
+            double gc0 = 0.0, gs0 = 0.0, gc1 = 0.0, gs1 = 0.0;
             {
-                if (ph == 0 && base >= RING && m < N) {
-                    if (role == 0) pend = t[m];
-                    if (role == 1) pend = y ? y[m] : (philox ? philox_normal(A.seed, seq, (uint64_t)m) : 0.0);
-                    if (role == 2) pend = dg ? dg[m] : 0.0;
+                const double *Pp = &sm.P[par][0][k0];
+                int s = 0;
+                for (; s + 1 <= nsb; s += 2) {
+                    const double2 v0 = *reinterpret_cast<const double2 *>(Pp + s * JP_MAX);
+                    const double2 v1 = *reinterpret_cast<const double2 *>(Pp + (s + 1) * JP_MAX);
+                    gc0 += v0.x; gs0 += v0.y; gc1 += v1.x; gs1 += v1.y;
                 }
-                if (ph == 1 && base >= RING && m < N) {
-                    if (role == 0) sm.tbuf[m & (RING - 1)] = pend;
-                    if (role == 1) sm.ybuf[m & (RING - 1)] = pend;
-                    if (role == 2) sm.dbuf[m & (RING - 1)] = pend;
+                if (s <= nsb) {
+                    const double2 v0 = *reinterpret_cast<const double2 *>(Pp + s * JP_MAX);
+                    gc0 += v0.x; gs0 += v0.y;
+                }
+            }
+            double qf = 0.0;
+            {
+                const double2 *Q2 = reinterpret_cast<const double2 *>(&sm.QF[par][0]);
+                const double2 a0 = Q2[0], a1 = Q2[1], a2 = Q2[2], a3 = Q2[3];
+                qf = ((a0.x + a0.y) + (a1.x + a1.y)) + ((a2.x + a2.y) + (a3.x + a3.y));
+            }
+            const double2 vn = sm.RV[s0][tix];
+            const double kappa = dprev * alpha;
+            const double beta = fma(kappa, alpha, qf);
+            const double dn = sm.Ra[s0] - beta;
+            if (!(dn > 0.0)) {
+                // not positive definite: stop the matrix warps at phase n + 2, absorb the
+                // arrival of phase n + 1 (already released), then only keep the ring
+                // hand-shake with the producer going until the natural end
+                fail = (int32_t)(n + 1);
+                if (ht == 0) sm.stop = n + 2;
+                if (n + 2 < N) bar_arrive(BAR_OPS + par, N_OPS);
+                if (n + 1 < N) bar_sync(BAR_PART + (par ^ 1), N_OPS);
+                drain = true;
+            } else {
+                const double rd = 1.0 / dn;
+                const double hc = fma(kappa, wc, gc0 + gc1), hs = fma(kappa, ws, gs0 + gs1);
+                double wcn = (vn.x - hc) * rd, wsn = (vn.y - hs) * rd;   // w~_n, frame of step n
+                if (!act) { wcn = 0.0; wsn = 0.0; }
+                const double r1 = act ? sm.Rr[s1][tix] : 1.0;
+                if (MODE == MODE_FACTOR && A.out_W && act) {
+                    const double qn = sm.Rq[s0][tix];
+                    double *Wn = A.out_W + A.w_off[b] + n * (long long)J;
+                    Wn[term] = wcn * qn;
+                    Wn[Jc + term] = wsn * qn;
+                }
+                const double wc1 = wcn * r1, ws1 = wsn * r1;             // frame of step n + 1
+                // operands of matrix phase n + 2: row n + 2 and the rank-1 term of step n
+                if (n + 2 < N) {
+                    if (act) {
+                        const double2 u2 = sm.RU[s2][tix];
+                        const double r2 = sm.Rr[s2][tix];
+                        sm.A[par][ke][kb] = make_double2(u2.x, dn * wc1);
+                        sm.A[par][ke + 1][kb] = make_double2(u2.y, dn * ws1);
+                        sm.C[par][ke][kb] = make_double2(u2.x, wc1);
+                        sm.C[par][ke + 1][kb] = make_double2(u2.y, ws1);
+                        *reinterpret_cast<double2 *>(&sm.R[par][k0]) = make_double2(r2, r2);
+                    }
+                    if (ht == 0) sm.renorm[par] = sm.Rflag[s2];
+                    bar_arrive(BAR_OPS + par, N_OPS);
+                }
+                // ---- off the critical path ------------------------------------------------
+                double zp;
+                if (MODE == MODE_LOGLIKE) {
+                    const double zn = sm.Ry[s0] - gamma;
+                    quad = fma(zn * zn, rd, quad);
+                    zp = zn;
+                } else if (MODE == MODE_SAMPLE) {
+                    zp = sm.Ry[s0] * sqrt(dn);
+                    if (ht == 0) A.out_x[n0 + n] = zp + gamma;
+                } else {
+                    zp = 0.0;
+                    if (ht == 0) A.out_x[n0 + n] = dn;
+                }
+                prod *= dn;
+                if ((n & 7) == 7) { if (ht == 0) logdet += log(prod); prod = 1.0; }
+                Fc = fma(wcn, zp, Fc) * r1; Fs = fma(wsn, zp, Fs) * r1;   // F~_{n+1}, frame n + 1
+                wc = wc1; ws = ws1; dprev = dn;
+                if (n + 1 < N) {
+                    const double2 u1 = sm.RU[s1][tix];
+                    alpha = act ? (u1.x * wc + u1.y * ws) : 0.0;
+                    gamma = act ? (u1.x * Fc + u1.y * Fs) : 0.0;
+                    chain_reduce2(sm, par, hw, lane, alpha, gamma);
                 }
             }
         }
-
-        bar_sync(BAR_PART + par, FT_THREADS);
-        double gc = 0.0, gs = 0.0;
-        if (act) {
-            for (int s = 0; s <= nsb; ++s) {
-                const double2 v = *reinterpret_cast<const double2 *>(&sm.P[par][s][k0]);
-                gc += v.x; gs += v.y;
-            }
-        }
-        const double hc = fma(kappa, wc, gc), hs = fma(kappa, ws, gs);
-        double beta = hc * r0.uc + hs * r0.us;
-        double gamma = r0.uc * Fc + r0.us * Fs;
-        hreduce2(sm, par, hw, lane, beta, gamma);
-
-        const int slot = (int)(n & (RING - 1));
-        const double an = (sm.dbuf[slot] + ddiag) + sum_a;
-        const double dn = an - beta;
-        if (!(dn > 0.0)) {
-            // not positive definite: stop the matrix warps at phase n + 2 and absorb the
-            // arrival of phase n + 1 (already released) so that the barriers end up balanced
-            fail = (int32_t)(n + 1);
-            if (ht == 0) sm.stop = n + 2;
-            if (n + 2 < N) bar_arrive(BAR_OPS + par, FT_THREADS);
-            if (n + 1 < N) bar_sync(BAR_PART + (par ^ 1), FT_THREADS);
-            break;
-        }
-        const double rd = 1.0 / dn;
-        double wcn = (r0.vc - hc) * rd, wsn = (r0.vs - hs) * rd;   // w~_n, frame of step n
-        double zp;
-        if (MODE == MODE_LOGLIKE) {
-            const double zn = sm.ybuf[slot] - gamma;
-            quad = fma(zn * zn, rd, quad);
-            zp = zn;
-        } else if (MODE == MODE_SAMPLE) {
-            zp = sm.ybuf[slot] * sqrt(dn);
-            if (ht == 0) A.out_x[n0 + n] = zp + gamma;
-        } else {
-            zp = 0.0;
-            if (ht == 0) A.out_x[n0 + n] = dn;
-            if (A.out_W && act) {
-                double *Wn = A.out_W + A.w_off[b] + n * (long long)J;
-                Wn[term] = wcn * r0.q;
-                Wn[Jc + term] = wsn * r0.q;
-            }
-        }
-        prod *= dn;
-        if ((n & 7) == 7) { if (hw == 0) logdet += log(prod); prod = 1.0; }
-        Fc = fma(wcn, zp, Fc); Fs = fma(wsn, zp, Fs);
-        // into the frame of step n + 1
-        wcn *= r1.r; wsn *= r1.r; Fc *= r1.r; Fs *= r1.r;
-
-        // operands of matrix phase n + 2: row n + 2 and the rank-1 term of step n
-        if (n + 2 < N) {
-            if (act) {
-                sm.A[par][ke][kb] = make_double2(r2.uc, dn * wcn);
-                sm.A[par][ke + 1][kb] = make_double2(r2.us, dn * wsn);
-                sm.C[par][ke][kb] = make_double2(r2.uc, wcn);
-                sm.C[par][ke + 1][kb] = make_double2(r2.us, wsn);
-                sm.R[par][k0] = r2.r; sm.R[par][k0 + 1] = r2.r;
-            }
-            if (ht == 0) sm.renorm[par] = r2.flag;
-            bar_arrive(BAR_OPS + par, FT_THREADS);
-        }
-        wc = wcn; ws = wsn;
-        if (n + 1 < N) {
-            double alpha = r1.uc * wc + r1.us * ws;
-            hreduce1(sm, par, hw, lane, alpha);
-            kappa = dn * alpha;
-        }
-        r0 = r1; r1 = r2;
-        const long long m3 = n + 3;
-        r2 = gen.make(m3 < N ? sm.tbuf[m3 & (RING - 1)] : 0.0, m3, act && m3 < N);
-        r2.flag = __shfl_sync(0xffffffffu, r2.flag, 0);
+        // ring hand-over: row n is dead now
+        if ((n & (HALF - 1)) == HALF - 1 && n / HALF + 2 < nh)
+            bar_arrive(BAR_EMPTY + (int)((n / HALF) & 1), N_RING);
     }
     if (ht == 0) {
         if (prod != 1.0) logdet += log(prod);
@@ -462,7 +564,7 @@ __device__ __forceinline__ void vector_loop(FastSmem &sm, const ScanArgs &A, con
     }
 }
 
-// Per-sequence prologue shared by both roles: claim the next sequence, clear the buffers.
+// Per-sequence prologue shared by all roles: claim the next sequence, clear the buffers.
 // Returns false when the queue is empty.
 struct SeqInfo {
     int b, Jc, nsb;
@@ -498,8 +600,8 @@ __global__ void __launch_bounds__(FT_THREADS, 1) scan_fast_kernel(ScanArgs A)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FastSmem &sm = *reinterpret_cast<FastSmem *>(smem_raw);
     const int tid = threadIdx.x;
-    // the two roles never rejoin: each has its own persistent loop, so that the register
-    // budgets set by setmaxnreg apply to the whole role
+    // the roles never rejoin: each has its own persistent loop, so that the register budgets
+    // set by setmaxnreg apply to the whole role
     if (tid < MAT_THREADS) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REG_MAT));
         SeqInfo q;
@@ -508,14 +610,21 @@ __global__ void __launch_bounds__(FT_THREADS, 1) scan_fast_kernel(ScanArgs A)
         }
     } else {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REG_HLP));
+        const int ht = tid - MAT_THREADS;
         SeqInfo q;
-        while (next_sequence(sm, A, tid, q)) {
-            if (q.N > 0) {
-                vector_loop<MODE>(sm, A, tid - MAT_THREADS, q.b, q.nsb, q.N, q.Jc);
-            } else if (tid == MAT_THREADS) {
-                A.logdet[q.b] = 0.0;
-                if (A.quad) A.quad[q.b] = 0.0;
-                A.status[q.b] = 0;
+        if (ht < CH_THREADS) {
+            while (next_sequence(sm, A, tid, q)) {
+                if (q.N > 0) {
+                    chain_loop<MODE>(sm, A, ht, q.b, q.nsb, q.N, q.Jc);
+                } else if (ht == 0) {
+                    A.logdet[q.b] = 0.0;
+                    if (A.quad) A.quad[q.b] = 0.0;
+                    A.status[q.b] = 0;
+                }
+            }
+        } else {
+            while (next_sequence(sm, A, tid, q)) {
+                if (q.N > 0) producer_loop<MODE>(sm, A, ht - CH_THREADS, q.b, q.N, q.Jc);
             }
         }
     }

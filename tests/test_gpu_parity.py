@@ -67,7 +67,12 @@ def test_batched_mixed_widths_shared_and_ragged(solver, solar_kernel, giant_kern
     ts = [np.sort(rng.uniform(0, n * 9e-5, n)) for n in lengths]
     ts = [np.cumsum(np.maximum(np.diff(t, prepend=0.0), 6.1e-5)) for t in ts]
     ys = [rng.standard_normal(n) * 50 for n in lengths]
-    diags = [np.full(n, 0.5 + b) for b, n in enumerate(lengths)]
+    # white-noise floor of 1e-4 k(0): with a negligible floor the giant's covariance is so
+    # ill-conditioned (d_n / a_n ~ 1e-7) that one-ulp differences in sin/cos already move log det
+    # by 1e-9 -- for the oracle as much as for the GPU path (see test_ill_conditioned_...)
+    k0s = [np.sum(k.scan_coefficients()[0]) + np.sum(k.scan_coefficients()[2]) + k.scan_coefficients()[6]
+           for k in kernels]
+    diags = [np.full(n, 1e-4 * k0 * (1 + b)) for b, (n, k0) in enumerate(zip(lengths, k0s))]
     t, y, dg = map(np.concatenate, (ts, ys, diags))
     ll, logdet, quad, status = batch.log_likelihood(kernels, t, y, dg, lengths=lengths, solver=solver,
                                                     return_parts=True, flags=flags)
