@@ -164,6 +164,7 @@ int check_geometry(gf_handle h, int64_t B, const int64_t *n_off, const int64_t *
         int64_t N = n_off[b + 1] - n_off[b];
         int64_t Jc = j_off[b + 1] - j_off[b];
         if (N < 0 || Jc < 0) return fail(h, GF_E_ARG, "offsets must be non-decreasing");
+        if (N > 0x7fffff00LL) return fail(h, GF_E_ARG, "a sequence is limited to 2^31 - 256 samples");
         if (2 * Jc > GF_MAX_J) return fail(h, GF_E_TOO_WIDE, "state wider than GF_MAX_J");
         if (t_off[b] < 0 || t_off[b] + N > t_len) return fail(h, GF_E_ARG, "t_off out of range");
         g->jmax = std::max(g->jmax, (int)(2 * Jc));

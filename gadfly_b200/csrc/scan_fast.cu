@@ -84,7 +84,7 @@ struct FastSmem {
     double2 Kcd[JC_MAX + 8];        // per-term (c, d)
     double2 Kp[JC_MAX + 8];         // per-term cached decay over the cadence dt0: (p0, 1 / p0)
     int renorm[2];
-    long long stop;                 // first matrix phase that must not run
+    int stop;                       // first matrix phase that must not run
     int next;
 };
 
@@ -167,13 +167,105 @@ __device__ __forceinline__ TileMap make_tile_map(int mt, int nsb)
     return m;
 }
 
-__device__ __forceinline__ void matrix_loop(FastSmem &sm, const int mt, const int nsb,
-                                            const long long N)
+template <int PAR>
+__device__ __forceinline__ void matrix_step(FastSmem &sm, double (&S)[TILE][TILE], const TileMap &tm,
+                                            const double qw, const int lane, const int warp)
+{
+    const int bi = tm.bi, bj = tm.bj;
+    double uj[TILE], wj[TILE];
+#pragma unroll
+    for (int e = 0; e < TILE; ++e) {
+        const double2 c = sm.C[PAR][e][bj];
+        uj[e] = c.x; wj[e] = c.y;
+    }
+    if (sm.renorm[PAR]) {
+        // frame change: S~ <- r r^T o (S~ + d w~ w~^T); the rank-1 term is consumed here
+#pragma unroll
+        for (int i = 0; i < TILE; ++i) {
+            const double dwi = sm.A[PAR][i][bi].y;
+            const double rgi = sm.R[PAR][bi * TILE + i];
+#pragma unroll
+            for (int j = 0; j < TILE; ++j) {
+                const double rgj = sm.R[PAR][bj * TILE + j];
+                S[i][j] = (rgi * fma(dwi, wj[j], S[i][j])) * rgj;
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < TILE; ++e) wj[e] = 0.0;
+    }
+
+    // rank-1 update fused with the two partial matrix-vector products; two rows at a time so
+    // that the two row accumulators and the eight column accumulators are independent chains
+    double colp[TILE], rowp[TILE];
+#pragma unroll
+    for (int e = 0; e < TILE; ++e) colp[e] = 0.0;
+#pragma unroll
+    for (int i = 0; i < TILE; i += 2) {
+        const double2 a0 = sm.A[PAR][i][bi], a1 = sm.A[PAR][i + 1][bi];
+        double rp0 = 0.0, rp1 = 0.0;
+#pragma unroll
+        for (int j = 0; j < TILE; ++j) {
+            const double T0 = fma(a0.y, wj[j], S[i][j]);
+            const double T1 = fma(a1.y, wj[j], S[i + 1][j]);
+            S[i][j] = T0; S[i + 1][j] = T1;
+            colp[j] = fma(a0.x, T0, colp[j]);
+            rp0 = fma(T0, uj[j], rp0);
+            colp[j] = fma(a1.x, T1, colp[j]);
+            rp1 = fma(T1, uj[j], rp1);
+        }
+        rowp[i] = rp0; rowp[i + 1] = rp1;
+    }
+
+    // quadratic form u~ S~ u~^T: this tile's share, reduced over the warp
+    double qf0 = colp[0] * uj[0], qf1 = colp[1] * uj[1];
+#pragma unroll
+    for (int j = 2; j < TILE; j += 2) { qf0 = fma(colp[j], uj[j], qf0); qf1 = fma(colp[j + 1], uj[j + 1], qf1); }
+    double qf = (qf0 + qf1) * qw;
+
+    // 2x2 group: combine the two tiles of a block row (lane ^ 1) and of a block column
+    // (lane ^ 2); each lane keeps four of the eight sums
+    double rs[4], cs[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const double send_r = tm.cj ? rowp[q] : rowp[4 + q];
+        const double keep_r = tm.cj ? rowp[4 + q] : rowp[q];
+        rs[q] = keep_r + shfl_xor_d(send_r, 1);
+        const double send_c = tm.ri ? colp[q] : colp[4 + q];
+        const double keep_c = tm.ri ? colp[4 + q] : colp[q];
+        cs[q] = keep_c + shfl_xor_d(send_c, 2);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) qf += shfl_xor_d(qf, off);
+    if (lane == 0) sm.QF[PAR][warp] = qf;
+
+    if (tm.kind == 0) {
+        double *pr = &sm.P[PAR][tm.slot_row][bi * TILE + tm.cj * 4];
+        double *pc = &sm.P[PAR][tm.slot_col][bj * TILE + tm.ri * 4];
+        *reinterpret_cast<double2 *>(pr) = make_double2(rs[0], rs[1]);
+        *reinterpret_cast<double2 *>(pr + 2) = make_double2(rs[2], rs[3]);
+        *reinterpret_cast<double2 *>(pc) = make_double2(cs[0], cs[1]);
+        *reinterpret_cast<double2 *>(pc + 2) = make_double2(cs[2], cs[3]);
+    } else if (tm.kind == 1) {
+        double *pc = &sm.P[PAR][tm.slot_col][bj * TILE];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<double2 *>(pc + 2 * q) = make_double2(colp[2 * q], colp[2 * q + 1]);
+    } else if (tm.kind == 2) {
+        double *pr = &sm.P[PAR][tm.slot_row][bi * TILE];
+        double *pc = &sm.P[PAR][tm.slot_col][bj * TILE];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            *reinterpret_cast<double2 *>(pr + 2 * q) = make_double2(rowp[2 * q], rowp[2 * q + 1]);
+            *reinterpret_cast<double2 *>(pc + 2 * q) = make_double2(colp[2 * q], colp[2 * q + 1]);
+        }
+    }
+}
+
+__device__ __forceinline__ void matrix_loop(FastSmem &sm, const int mt, const int nsb, const int N)
 {
     const TileMap tm = make_tile_map(mt, nsb);
-    const int bi = tm.bi, bj = tm.bj;
     // weight of this tile in the quadratic form: off-diagonal tiles stand for their mirror too
-    const double qw = (tm.kind == 3) ? 0.0 : ((bi == bj) ? 1.0 : 2.0);
+    const double qw = (tm.kind == 3) ? 0.0 : ((tm.bi == tm.bj) ? 1.0 : 2.0);
     const int lane = mt & 31, warp = mt >> 5;
     double S[TILE][TILE];
 #pragma unroll
@@ -181,95 +273,19 @@ __device__ __forceinline__ void matrix_loop(FastSmem &sm, const int mt, const in
 #pragma unroll
         for (int j = 0; j < TILE; ++j) S[i][j] = 0.0;
 
-    for (long long n = 0; n < N; ++n) {
-        const int par = (int)(n & 1);
-        bar_sync(BAR_OPS + par, N_OPS);
-        if (n >= sm.stop) break;
-
-        double uj[TILE], wj[TILE];
-#pragma unroll
-        for (int e = 0; e < TILE; ++e) {
-            const double2 c = sm.C[par][e][bj];
-            uj[e] = c.x; wj[e] = c.y;
-        }
-        if (sm.renorm[par]) {
-            // frame change: S~ <- r r^T o (S~ + d w~ w~^T); the rank-1 term is consumed here
-#pragma unroll
-            for (int i = 0; i < TILE; ++i) {
-                const double dwi = sm.A[par][i][bi].y;
-                const double rgi = sm.R[par][bi * TILE + i];
-#pragma unroll
-                for (int j = 0; j < TILE; ++j) {
-                    const double rgj = sm.R[par][bj * TILE + j];
-                    S[i][j] = (rgi * fma(dwi, wj[j], S[i][j])) * rgj;
-                }
-            }
-#pragma unroll
-            for (int e = 0; e < TILE; ++e) wj[e] = 0.0;
-        }
-
-        double colp[TILE], rowp[TILE];
-#pragma unroll
-        for (int e = 0; e < TILE; ++e) { colp[e] = 0.0; rowp[e] = 0.0; }
-#pragma unroll
-        for (int i = 0; i < TILE; ++i) {
-            const double2 a = sm.A[par][i][bi];
-            const double ui = a.x, dwi = a.y;
-            double rp = 0.0;
-#pragma unroll
-            for (int j = 0; j < TILE; ++j) {
-                const double T = fma(dwi, wj[j], S[i][j]);
-                S[i][j] = T;
-                colp[j] = fma(ui, T, colp[j]);
-                rp = fma(T, uj[j], rp);
-            }
-            rowp[i] = rp;
-        }
-
-        // quadratic form u~ S~ u~^T: this tile's share, reduced over the warp
-        double qf = 0.0;
-#pragma unroll
-        for (int j = 0; j < TILE; ++j) qf = fma(colp[j], uj[j], qf);
-        qf *= qw;
-
-        // 2x2 group: combine the two tiles of a block row (lane ^ 1) and of a block column
-        // (lane ^ 2); each lane keeps four of the eight sums
-        double rs[4], cs[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const double send_r = tm.cj ? rowp[q] : rowp[4 + q];
-            const double keep_r = tm.cj ? rowp[4 + q] : rowp[q];
-            rs[q] = keep_r + shfl_xor_d(send_r, 1);
-            const double send_c = tm.ri ? colp[q] : colp[4 + q];
-            const double keep_c = tm.ri ? colp[4 + q] : colp[q];
-            cs[q] = keep_c + shfl_xor_d(send_c, 2);
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) qf += shfl_xor_d(qf, off);
-        if (lane == 0) sm.QF[par][warp] = qf;
-
-        if (tm.kind == 0) {
-            double *pr = &sm.P[par][tm.slot_row][bi * TILE + tm.cj * 4];
-            double *pc = &sm.P[par][tm.slot_col][bj * TILE + tm.ri * 4];
-            *reinterpret_cast<double2 *>(pr) = make_double2(rs[0], rs[1]);
-            *reinterpret_cast<double2 *>(pr + 2) = make_double2(rs[2], rs[3]);
-            *reinterpret_cast<double2 *>(pc) = make_double2(cs[0], cs[1]);
-            *reinterpret_cast<double2 *>(pc + 2) = make_double2(cs[2], cs[3]);
-        } else if (tm.kind == 1) {
-            double *pc = &sm.P[par][tm.slot_col][bj * TILE];
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                *reinterpret_cast<double2 *>(pc + 2 * q) = make_double2(colp[2 * q], colp[2 * q + 1]);
-        } else if (tm.kind == 2) {
-            double *pr = &sm.P[par][tm.slot_row][bi * TILE];
-            double *pc = &sm.P[par][tm.slot_col][bj * TILE];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                *reinterpret_cast<double2 *>(pr + 2 * q) = make_double2(rowp[2 * q], rowp[2 * q + 1]);
-                *reinterpret_cast<double2 *>(pc + 2 * q) = make_double2(colp[2 * q], colp[2 * q + 1]);
-            }
-        }
-        bar_arrive(BAR_PART + par, N_OPS);
+    const volatile int *stop = &sm.stop;
+    int n = 0;
+    for (;;) {
+        bar_sync(BAR_OPS + 0, N_OPS);
+        if (n >= *stop) break;
+        matrix_step<0>(sm, S, tm, qw, lane, warp);
+        bar_arrive(BAR_PART + 0, N_OPS);
+        if (++n >= N) break;
+        bar_sync(BAR_OPS + 1, N_OPS);
+        if (n >= *stop) break;
+        matrix_step<1>(sm, S, tm, qw, lane, warp);
+        bar_arrive(BAR_PART + 1, N_OPS);
+        if (++n >= N) break;
     }
 }
 
@@ -406,160 +422,201 @@ __device__ __forceinline__ void producer_loop(FastSmem &sm, const ScanArgs &A, c
 // ------------------------------------------------------------------------------------------
 // chain warps
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void chain_reduce2(FastSmem &sm, int par, int hw, int lane, double &a, double &b)
+// 1 / d for a positive normal d: hardware seed (20 bits) + two Newton steps, branch-free
+__device__ __forceinline__ double fast_rcp(double d)
 {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) { a += shfl_xor_d(a, off); b += shfl_xor_d(b, off); }
-    if (lane == 0) sm.red2[par][hw] = make_double2(a, b);
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+    double e = fma(-d, x, 1.0);
+    x = fma(x, e, x);
+    e = fma(-d, x, 1.0);
+    x = fma(x, e, x);
+    return x;
+}
+
+// Sum (a, b) over the three chain warps.  The first butterfly stage transposes: afterwards the
+// low half-warp carries a and the high half-warp b, so four more stages finish both.
+template <int PAR>
+__device__ __forceinline__ void chain_reduce2(FastSmem &sm, int hw, int lane, double &a, double &b)
+{
+    const bool hi = (lane & 16) != 0;
+    const double send = hi ? a : b, keep = hi ? b : a;
+    double v = keep + shfl_xor_d(send, 16);
+    v += shfl_xor_d(v, 8);
+    v += shfl_xor_d(v, 4);
+    v += shfl_xor_d(v, 2);
+    v += shfl_xor_d(v, 1);
+    if ((lane & 15) == 0) reinterpret_cast<double *>(&sm.red2[PAR][hw])[lane >> 4] = v;
     bar_sync(BAR_CH, CH_THREADS);
-    const double2 v0 = sm.red2[par][0], v1 = sm.red2[par][1], v2 = sm.red2[par][2];
+    const double2 v0 = sm.red2[PAR][0], v1 = sm.red2[PAR][1], v2 = sm.red2[PAR][2];
     a = (v0.x + v1.x) + v2.x;
     b = (v0.y + v1.y) + v2.y;
 }
 
+struct ChainState {
+    double wc, ws;          // w~_{n-1}, in the frame of step n
+    double Fc, Fs;          // F~_n of this term, frame of step n
+    double alpha, gamma;    // u~_n . w~_{n-1},  u~_n . F~_n
+    double kappa;           // d_{n-1} alpha_n
+    double logdet, prod, quad;
+};
+
+struct ChainConst {
+    int ht, hw, lane, term, tix, k0, kb, ke, Jc, J, N, b;
+    bool act;
+    long long n0;
+};
+
+// One time step of the chain.  Returns false when the pivot is not positive.
+template <int MODE, int PAR>
+__device__ __forceinline__ bool chain_step(FastSmem &sm, const ScanArgs &A, ChainState &st,
+                                           const ChainConst &c, const int n)
+{
+    const int s0 = n & (RR - 1), s1 = (n + 1) & (RR - 1), s2 = (n + 2) & (RR - 1);
+    const int tix = c.tix;
+    bar_sync(BAR_PART + PAR, N_OPS);
+    // everything this step reads, issued up front
+    double2 v[NSLOT];
+    {
+        const double2 *Pp = reinterpret_cast<const double2 *>(&sm.P[PAR][0][0]) + tix;
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) v[s] = Pp[s * (JP_MAX / 2)];
+    }
+    const double2 *Q2 = reinterpret_cast<const double2 *>(&sm.QF[PAR][0]);
+    const double2 q0 = Q2[0], q1 = Q2[1], q2 = Q2[2], q3 = Q2[3];
+    const double2 vn = sm.RV[s0][tix];
+    const double ra = sm.Ra[s0], yn = sm.Ry[s0];
+    const double r1 = sm.Rr[s1][tix];
+    const double2 u1 = sm.RU[s1][tix];
+    const double2 u2 = sm.RU[s2][tix];
+    const double r2 = sm.Rr[s2][tix];
+
+    // pivot: d_n = a_n - (u~ S~(n-1) u~^T + d_{n-1} alpha_n^2)
+    const double qf = ((q0.x + q0.y) + (q1.x + q1.y)) + ((q2.x + q2.y) + (q3.x + q3.y));
+    const double dn = ra - fma(st.kappa, st.alpha, qf);
+    if (!(dn > 0.0)) return false;
+    const double rd = fast_rcp(dn);
+    // g_n: unused slots hold zeros, so the sum always runs over all of them
+    static_assert(NSLOT == 12, "summation tree below is written for 12 slots");
+    const double gc = (((v[0].x + v[1].x) + (v[2].x + v[3].x)) + ((v[4].x + v[5].x) + (v[6].x + v[7].x))) +
+                      ((v[8].x + v[9].x) + (v[10].x + v[11].x));
+    const double gs = (((v[0].y + v[1].y) + (v[2].y + v[3].y)) + ((v[4].y + v[5].y) + (v[6].y + v[7].y))) +
+                      ((v[8].y + v[9].y) + (v[10].y + v[11].y));
+    const double hc = fma(st.kappa, st.wc, gc), hs = fma(st.kappa, st.ws, gs);
+    const double tc = vn.x - hc, ts = vn.y - hs;            // d_n w~_n, frame of step n
+    const double wcn = tc * rd, wsn = ts * rd;              // w~_n
+    const double wc1 = wcn * r1, ws1 = wsn * r1;            // frame of step n + 1
+    // operands of matrix phase n + 2: row n + 2 and the rank-1 term of step n
+    if (n + 2 < c.N) {
+        if (c.act) {
+            sm.A[PAR][c.ke][c.kb] = make_double2(u2.x, tc * r1);
+            sm.A[PAR][c.ke + 1][c.kb] = make_double2(u2.y, ts * r1);
+            sm.C[PAR][c.ke][c.kb] = make_double2(u2.x, wc1);
+            sm.C[PAR][c.ke + 1][c.kb] = make_double2(u2.y, ws1);
+            *reinterpret_cast<double2 *>(&sm.R[PAR][c.k0]) = make_double2(r2, r2);
+        }
+        if (c.ht == 0) sm.renorm[PAR] = sm.Rflag[s2];
+        bar_arrive(BAR_OPS + PAR, N_OPS);
+    }
+    // ---- off the critical path ------------------------------------------------------------
+    if (MODE == MODE_FACTOR && A.out_W && c.act) {
+        const double qn = sm.Rq[s0][tix];
+        double *Wn = A.out_W + A.w_off[c.b] + (long long)n * c.J;
+        Wn[c.term] = wcn * qn;
+        Wn[c.Jc + c.term] = wsn * qn;
+    }
+    double zp;
+    if (MODE == MODE_LOGLIKE) {
+        const double zn = yn - st.gamma;
+        st.quad = fma(zn * zn, rd, st.quad);
+        zp = zn;
+    } else if (MODE == MODE_SAMPLE) {
+        zp = yn * sqrt(dn);
+        if (c.ht == 0) A.out_x[c.n0 + n] = zp + st.gamma;
+    } else {
+        zp = 0.0;
+        if (c.ht == 0) A.out_x[c.n0 + n] = dn;
+    }
+    st.prod *= dn;
+    if ((n & 7) == 7) { if (c.ht == 0) st.logdet += log(st.prod); st.prod = 1.0; }
+    st.Fc = fma(wcn, zp, st.Fc) * r1;                       // F~_{n+1}, frame of step n + 1
+    st.Fs = fma(wsn, zp, st.Fs) * r1;
+    st.wc = wc1; st.ws = ws1;
+    if (n + 1 < c.N) {
+        double alpha = c.act ? fma(u1.x, wc1, u1.y * ws1) : 0.0;
+        double gamma = c.act ? fma(u1.x, st.Fc, u1.y * st.Fs) : 0.0;
+        chain_reduce2<PAR>(sm, c.hw, c.lane, alpha, gamma);
+        st.alpha = alpha; st.gamma = gamma; st.kappa = dn * alpha;
+    }
+    return true;
+}
+
 template <int MODE>
 __device__ __forceinline__ void chain_loop(FastSmem &sm, const ScanArgs &A, const int ht,
-                                           const int b, const int nsb, const long long N,
-                                           const int Jc)
+                                           const int b, const int N, const int Jc)
 {
-    const int hw = ht >> 5, lane = ht & 31;
-    const int term = hw * TPW + lane;
-    const bool act = (lane < TPW) && (term < Jc);
-    const int tix = act ? term : 0;          // safe index for ring reads
-    const int k0 = 2 * tix;                  // cos column; sin column is k0 + 1
-    const int kb = k0 >> 3, ke = k0 & 7;     // both columns sit in block kb (ke is even)
-    const long long n0 = A.n_off[b];
-    const int J = 2 * Jc;
-    const long long nh = ring_halves(N);
+    ChainConst c;
+    c.ht = ht; c.hw = ht >> 5; c.lane = ht & 31;
+    c.term = c.hw * TPW + c.lane;
+    c.act = (c.lane < TPW) && (c.term < Jc);
+    c.tix = c.act ? c.term : 0;              // inactive lanes shadow term 0 and store nothing
+    c.k0 = 2 * c.tix;                        // cos column; sin column is k0 + 1
+    c.kb = c.k0 >> 3; c.ke = c.k0 & 7;       // both columns sit in block kb (ke is even)
+    c.Jc = Jc; c.J = 2 * Jc; c.N = N; c.b = b;
+    c.n0 = A.n_off[b];
+    const int nh = (int)ring_halves(N);
+    const int tix = c.tix;
 
     bar_sync(BAR_FULL + 0, N_RING);          // ring half 0: rows 0..7
 
     // operands of matrix phases 0 and 1: rows 0 / 1, no rank-1 term yet
-    if (act) {
+    if (c.act) {
         const double2 u0 = sm.RU[0][tix], u1 = sm.RU[1][tix];
-        sm.A[0][ke][kb] = make_double2(u0.x, 0.0);     sm.C[0][ke][kb] = make_double2(u0.x, 0.0);
-        sm.A[0][ke + 1][kb] = make_double2(u0.y, 0.0); sm.C[0][ke + 1][kb] = make_double2(u0.y, 0.0);
-        sm.A[1][ke][kb] = make_double2(u1.x, 0.0);     sm.C[1][ke][kb] = make_double2(u1.x, 0.0);
-        sm.A[1][ke + 1][kb] = make_double2(u1.y, 0.0); sm.C[1][ke + 1][kb] = make_double2(u1.y, 0.0);
-        sm.R[0][k0] = 1.0; sm.R[0][k0 + 1] = 1.0;
+        sm.A[0][c.ke][c.kb] = make_double2(u0.x, 0.0);     sm.C[0][c.ke][c.kb] = make_double2(u0.x, 0.0);
+        sm.A[0][c.ke + 1][c.kb] = make_double2(u0.y, 0.0); sm.C[0][c.ke + 1][c.kb] = make_double2(u0.y, 0.0);
+        sm.A[1][c.ke][c.kb] = make_double2(u1.x, 0.0);     sm.C[1][c.ke][c.kb] = make_double2(u1.x, 0.0);
+        sm.A[1][c.ke + 1][c.kb] = make_double2(u1.y, 0.0); sm.C[1][c.ke + 1][c.kb] = make_double2(u1.y, 0.0);
+        sm.R[0][c.k0] = 1.0; sm.R[0][c.k0 + 1] = 1.0;
         const double r1 = sm.Rr[1][tix];
-        sm.R[1][k0] = r1; sm.R[1][k0 + 1] = r1;
+        sm.R[1][c.k0] = r1; sm.R[1][c.k0 + 1] = r1;
     }
     if (ht == 0) { sm.renorm[0] = 0; sm.renorm[1] = (N > 1) ? sm.Rflag[1] : 0; }
     bar_arrive(BAR_OPS + 0, N_OPS);
     if (N > 1) bar_arrive(BAR_OPS + 1, N_OPS);
 
-    double wc = 0.0, ws = 0.0;       // w~_{n-1}, in the frame of step n
-    double Fc = 0.0, Fs = 0.0;       // F~_n of this term, frame of step n
-    double alpha = 0.0, gamma = 0.0; // u~_n . w~_{n-1},  u~_n . F~_n
-    double dprev = 0.0;
-    double logdet = 0.0, prod = 1.0, quad = 0.0;
+    ChainState st;
+    st.wc = st.ws = st.Fc = st.Fs = st.alpha = st.gamma = st.kappa = 0.0;
+    st.logdet = 0.0; st.prod = 1.0; st.quad = 0.0;
     int32_t fail = 0;
     bool drain = false;
 
-    for (long long n = 0; n < N; ++n) {
-        const int par = (int)(n & 1);
-        const int s0 = (int)(n & (RR - 1)), s1 = (int)((n + 1) & (RR - 1)), s2 = (int)((n + 2) & (RR - 1));
-        // ring hand-over: row n + 2 is first touched here
+    for (int n = 0; n < N; ++n) {
+        // ring hand-over: row n + 2 is first touched in this step
         if (((n + 2) & (HALF - 1)) == 0 && (n + 2) / HALF < nh)
-            bar_sync(BAR_FULL + (int)(((n + 2) / HALF) & 1), N_RING);
-
+            bar_sync(BAR_FULL + (((n + 2) / HALF) & 1), N_RING);
         if (!drain) {
-            bar_sync(BAR_PART + par, N_OPS);
-            // g_n: sum of the partial products; two independent accumulators per column
-            double gc0 = 0.0, gs0 = 0.0, gc1 = 0.0, gs1 = 0.0;
-            {
-                const double *Pp = &sm.P[par][0][k0];
-                int s = 0;
-                for (; s + 1 <= nsb; s += 2) {
-                    const double2 v0 = *reinterpret_cast<const double2 *>(Pp + s * JP_MAX);
-                    const double2 v1 = *reinterpret_cast<const double2 *>(Pp + (s + 1) * JP_MAX);
-                    gc0 += v0.x; gs0 += v0.y; gc1 += v1.x; gs1 += v1.y;
-                }
-                if (s <= nsb) {
-                    const double2 v0 = *reinterpret_cast<const double2 *>(Pp + s * JP_MAX);
-                    gc0 += v0.x; gs0 += v0.y;
-                }
-            }
-            double qf = 0.0;
-            {
-                const double2 *Q2 = reinterpret_cast<const double2 *>(&sm.QF[par][0]);
-                const double2 a0 = Q2[0], a1 = Q2[1], a2 = Q2[2], a3 = Q2[3];
-                qf = ((a0.x + a0.y) + (a1.x + a1.y)) + ((a2.x + a2.y) + (a3.x + a3.y));
-            }
-            const double2 vn = sm.RV[s0][tix];
-            const double kappa = dprev * alpha;
-            const double beta = fma(kappa, alpha, qf);
-            const double dn = sm.Ra[s0] - beta;
-            if (!(dn > 0.0)) {
+            const bool ok = (n & 1) ? chain_step<MODE, 1>(sm, A, st, c, n)
+                                    : chain_step<MODE, 0>(sm, A, st, c, n);
+            if (!ok) {
                 // not positive definite: stop the matrix warps at phase n + 2, absorb the
                 // arrival of phase n + 1 (already released), then only keep the ring
                 // hand-shake with the producer going until the natural end
-                fail = (int32_t)(n + 1);
+                const int par = n & 1;
+                fail = n + 1;
                 if (ht == 0) sm.stop = n + 2;
                 if (n + 2 < N) bar_arrive(BAR_OPS + par, N_OPS);
                 if (n + 1 < N) bar_sync(BAR_PART + (par ^ 1), N_OPS);
                 drain = true;
-            } else {
-                const double rd = 1.0 / dn;
-                const double hc = fma(kappa, wc, gc0 + gc1), hs = fma(kappa, ws, gs0 + gs1);
-                double wcn = (vn.x - hc) * rd, wsn = (vn.y - hs) * rd;   // w~_n, frame of step n
-                if (!act) { wcn = 0.0; wsn = 0.0; }
-                const double r1 = act ? sm.Rr[s1][tix] : 1.0;
-                if (MODE == MODE_FACTOR && A.out_W && act) {
-                    const double qn = sm.Rq[s0][tix];
-                    double *Wn = A.out_W + A.w_off[b] + n * (long long)J;
-                    Wn[term] = wcn * qn;
-                    Wn[Jc + term] = wsn * qn;
-                }
-                const double wc1 = wcn * r1, ws1 = wsn * r1;             // frame of step n + 1
-                // operands of matrix phase n + 2: row n + 2 and the rank-1 term of step n
-                if (n + 2 < N) {
-                    if (act) {
-                        const double2 u2 = sm.RU[s2][tix];
-                        const double r2 = sm.Rr[s2][tix];
-                        sm.A[par][ke][kb] = make_double2(u2.x, dn * wc1);
-                        sm.A[par][ke + 1][kb] = make_double2(u2.y, dn * ws1);
-                        sm.C[par][ke][kb] = make_double2(u2.x, wc1);
-                        sm.C[par][ke + 1][kb] = make_double2(u2.y, ws1);
-                        *reinterpret_cast<double2 *>(&sm.R[par][k0]) = make_double2(r2, r2);
-                    }
-                    if (ht == 0) sm.renorm[par] = sm.Rflag[s2];
-                    bar_arrive(BAR_OPS + par, N_OPS);
-                }
-                // ---- off the critical path ------------------------------------------------
-                double zp;
-                if (MODE == MODE_LOGLIKE) {
-                    const double zn = sm.Ry[s0] - gamma;
-                    quad = fma(zn * zn, rd, quad);
-                    zp = zn;
-                } else if (MODE == MODE_SAMPLE) {
-                    zp = sm.Ry[s0] * sqrt(dn);
-                    if (ht == 0) A.out_x[n0 + n] = zp + gamma;
-                } else {
-                    zp = 0.0;
-                    if (ht == 0) A.out_x[n0 + n] = dn;
-                }
-                prod *= dn;
-                if ((n & 7) == 7) { if (ht == 0) logdet += log(prod); prod = 1.0; }
-                Fc = fma(wcn, zp, Fc) * r1; Fs = fma(wsn, zp, Fs) * r1;   // F~_{n+1}, frame n + 1
-                wc = wc1; ws = ws1; dprev = dn;
-                if (n + 1 < N) {
-                    const double2 u1 = sm.RU[s1][tix];
-                    alpha = act ? (u1.x * wc + u1.y * ws) : 0.0;
-                    gamma = act ? (u1.x * Fc + u1.y * Fs) : 0.0;
-                    chain_reduce2(sm, par, hw, lane, alpha, gamma);
-                }
             }
         }
         // ring hand-over: row n is dead now
         if ((n & (HALF - 1)) == HALF - 1 && n / HALF + 2 < nh)
-            bar_arrive(BAR_EMPTY + (int)((n / HALF) & 1), N_RING);
+            bar_arrive(BAR_EMPTY + ((n / HALF) & 1), N_RING);
     }
     if (ht == 0) {
-        if (prod != 1.0) logdet += log(prod);
-        A.logdet[b] = logdet;
-        if (MODE == MODE_LOGLIKE && A.quad) A.quad[b] = quad;
+        if (st.prod != 1.0) st.logdet += log(st.prod);
+        A.logdet[b] = st.logdet;
+        if (MODE == MODE_LOGLIKE && A.quad) A.quad[b] = st.quad;
         A.status[b] = fail;
     }
 }
@@ -568,7 +625,7 @@ __device__ __forceinline__ void chain_loop(FastSmem &sm, const ScanArgs &A, cons
 // Returns false when the queue is empty.
 struct SeqInfo {
     int b, Jc, nsb;
-    long long N;
+    int N;
 };
 
 __device__ __forceinline__ bool next_sequence(FastSmem &sm, const ScanArgs &A, const int tid, SeqInfo &q)
@@ -585,7 +642,7 @@ __device__ __forceinline__ bool next_sequence(FastSmem &sm, const ScanArgs &A, c
     const int item = sm.next;
     if (item >= A.B) return false;
     q.b = A.order[item];
-    q.N = A.n_off[q.b + 1] - A.n_off[q.b];
+    q.N = (int)(A.n_off[q.b + 1] - A.n_off[q.b]);
     q.Jc = (int)(A.j_off[q.b + 1] - A.j_off[q.b]);
     const int nb = (2 * q.Jc + TILE - 1) / TILE;
     q.nsb = (nb + 1) / 2;
@@ -615,7 +672,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) scan_fast_kernel(ScanArgs A)
         if (ht < CH_THREADS) {
             while (next_sequence(sm, A, tid, q)) {
                 if (q.N > 0) {
-                    chain_loop<MODE>(sm, A, ht, q.b, q.nsb, q.N, q.Jc);
+                    chain_loop<MODE>(sm, A, ht, q.b, q.N, q.Jc);
                 } else if (ht == 0) {
                     A.logdet[q.b] = 0.0;
                     if (A.quad) A.quad[q.b] = 0.0;
