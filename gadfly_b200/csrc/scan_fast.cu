@@ -53,6 +53,11 @@ constexpr int RR = 16;               // row ring depth (two halves)
 constexpr int HALF = 8;
 constexpr int REG_MAT = 208;
 constexpr int REG_HLP = 88;
+constexpr int REG_LAUNCH = 168;      // registers per thread at launch (65536 / 384, multiple of 8)
+// setmaxnreg.inc only draws on what the CTA's own warps released: the matrix warps would wait
+// forever if the helpers did not give back enough
+static_assert((REG_MAT - REG_LAUNCH) * MAT_THREADS <= (REG_LAUNCH - REG_HLP) * (FT_THREADS - MAT_THREADS),
+              "register re-balancing does not add up");
 constexpr double RENORM_LIMIT = 64.0;
 constexpr int RENORM_STEPS = 64;
 
@@ -64,6 +69,16 @@ constexpr int BAR_FULL = 6;    // 6, 7: ring half produced                      
 constexpr int BAR_EMPTY = 8;   // 8, 9: ring half consumed                       [chain -> producer]
 constexpr int N_OPS = CH_THREADS + MAT_THREADS;
 constexpr int N_RING = CH_THREADS + 32;
+
+// producer-warp scalars that are touched once per half or only on the exact path: kept in shared
+// memory so that the registers of the (88-register) producer hold the per-term state instead
+struct ProdScalars {
+    const double *t, *y, *dg;
+    unsigned long long seq, seed;
+    long long N, m_ref;
+    double sum_ad_a, ddiag, cmax, wmax, dt0, t_ref;
+    int philox;
+};
 
 struct FastSmem {
     double2 A[2][TILE][NB_MAX];     // (u~_n[k], d w~[k]) for k = 8 b + e, indexed [e][b]
@@ -83,6 +98,19 @@ struct FastSmem {
     double2 Kab[JC_MAX + 8];        // per-term (a', b')
     double2 Kcd[JC_MAX + 8];        // per-term (c, d)
     double2 Kp[JC_MAX + 8];         // per-term cached decay over the cadence dt0: (p0, 1 / p0)
+    // uniform-cadence fast path of the producer: per term and step count i = 0..HALF,
+    // (cos, sin)(d * (i dt)), exp(-c i dt), exp(+c i dt) for the cached cadence dt
+    // per-term state of the last produced row: decay of the current frame (q, 1/q), (cos, sin)
+    // and the rounded phase d t
+    double2 PBq[JC_MAX + 8];
+    double2 PBt[JC_MAX + 8];
+    double PBx[JC_MAX + 8];
+    double2 TabT[HALF + 1][JC_MAX + 8];   // (cos, sin)(d * (i dt))
+    double2 TabQ[HALF + 1][JC_MAX + 8];   // exp(-c i dt), exp(+c i dt)
+    // per step of the half being produced (written by lanes 0-7 of the producer warp)
+    double Ht[HALF], Hde[HALF], Hrde[HALF];
+    int Hcode[HALF];
+    ProdScalars ps;
     int renorm[2];
     int stop;                       // first matrix phase that must not run
     int next;
@@ -298,24 +326,42 @@ template <int MODE>
 __device__ __forceinline__ void producer_loop(FastSmem &sm, const ScanArgs &A, const int lane,
                                               const int b, const long long N, const int Jc)
 {
-    const long long n0 = A.n_off[b];
     const long long j0 = A.j_off[b];
-    const double *t = A.t + A.t_off[b];
-    const double *y = A.y ? A.y + n0 : nullptr;
-    const double *dg = A.diag ? A.diag + n0 : nullptr;
-    const double ddiag = A.ddiag[b];
-    const bool philox = (MODE == MODE_SAMPLE) && (A.y == nullptr);
-    const uint64_t seq = A.seq0 + (uint64_t)b;
-
-    // sum of a' in term order (as the oracle adds it); largest decay rate
-    double sum_a = 0.0, cmax = 0.0;
-    for (int j = 0; j < Jc; ++j) {
-        sum_a += A.coef[4 * (j0 + j)];
-        cmax = fmax(cmax, A.coef[4 * (j0 + j) + 2]);
+    ProdScalars &ps = sm.ps;
+    bool fast_allowed;
+    {
+        const long long n0 = A.n_off[b];
+        const double *t = A.t + A.t_off[b];
+        // sum of a' in term order (as the oracle adds it); largest decay rate and frequency
+        double sum_a = 0.0, cmax = 0.0, dmax = 0.0;
+        for (int j = 0; j < Jc; ++j) {
+            sum_a += A.coef[4 * (j0 + j)];
+            cmax = fmax(cmax, A.coef[4 * (j0 + j) + 2]);
+            dmax = fmax(dmax, fabs(A.coef[4 * (j0 + j) + 3]));
+        }
+        // uniform-cadence fast path: rows by angle addition / decay products from the tables of
+        // the cached cadence dtT.  Allowed while the rounded phases stay below 1e8 (their rounding
+        // error, which the fast path reproduces to first order, is then < 1.5e-8 rad).
+        fast_allowed = (N > 2 * HALF) && (dmax * fmax(fabs(t[0]), fabs(t[N - 1])) < 1.0e8);
+        if (lane == 0) {
+            ps.t = t;
+            ps.y = A.y ? A.y + n0 : nullptr;
+            ps.dg = A.diag ? A.diag + n0 : nullptr;
+            ps.seq = A.seq0 + (uint64_t)b;
+            ps.seed = A.seed;
+            ps.N = N;
+            ps.m_ref = 0;
+            ps.sum_ad_a = sum_a;
+            ps.ddiag = A.ddiag[b];
+            ps.cmax = cmax;
+            ps.wmax = fmax(cmax, dmax);
+            ps.dt0 = 0.0;       // cadence the cached decay factors p0 belong to (exact path)
+            ps.t_ref = 0.0;
+            ps.philox = ((MODE == MODE_SAMPLE) && (A.y == nullptr)) ? 1 : 0;
+        }
     }
     // this lane's terms: lane, lane + 32, lane + 64; their constants stay in shared memory
     constexpr int TPL = 3;
-    double q[TPL], qinv[TPL];
     bool act[TPL];
 #pragma unroll
     for (int k = 0; k < TPL; ++k) {
@@ -326,12 +372,17 @@ __device__ __forceinline__ void producer_loop(FastSmem &sm, const ScanArgs &A, c
         sm.Kab[term] = make_double2(cf.x, cf.y);
         sm.Kcd[term] = make_double2(cf.z, cf.w);
         sm.Kp[term] = make_double2(1.0, 1.0);
-        q[k] = 1.0; qinv[k] = 1.0;
+        sm.PBq[term] = make_double2(1.0, 1.0);
+        sm.PBt[term] = make_double2(1.0, 0.0);
+        sm.PBx[term] = 0.0;
     }
     __syncwarp();
-    double dt0 = 0.0;            // cadence the cached decay factors p0 belong to
-    double t_prev = 0.0, t_ref = 0.0;
-    long long m_ref = 0;
+    double t_prev = 0.0;
+    bool tab_ok = false;
+    int cooldown = 0;
+    double dtT = 0.0;
+    int K = RENORM_STEPS;        // renormalisation period [steps] of the fast path
+    int kb = 0;                  // steps since the last renormalisation at the last produced row
 
     // per-half input staging: lanes 0-7 t, 8-15 y (or normal), 16-23 diag
     auto load_half = [&](long long m0) -> double {
@@ -339,9 +390,14 @@ __device__ __forceinline__ void producer_loop(FastSmem &sm, const ScanArgs &A, c
         const long long m = m0 + (lane & 7);
         double v = 0.0;
         if (m < N) {
-            if (role == 0) v = t[m];
-            else if (role == 1) v = y ? y[m] : (philox ? philox_normal(A.seed, seq, (uint64_t)m) : 0.0);
-            else if (role == 2) v = dg ? dg[m] : 0.0;
+            if (role == 0) v = ps.t[m];
+            else if (role == 1) {
+                const double *y = ps.y;
+                v = y ? y[m] : (ps.philox ? philox_normal(ps.seed, ps.seq, (uint64_t)m) : 0.0);
+            } else if (role == 2) {
+                const double *dg = ps.dg;
+                v = dg ? dg[m] : 0.0;
+            }
         }
         return v;
     };
@@ -355,64 +411,206 @@ __device__ __forceinline__ void producer_loop(FastSmem &sm, const ScanArgs &A, c
         if (hi >= 2) bar_sync(BAR_EMPTY + h, N_RING);
         const bool aborted = sm.stop < N;    // the chain gave up: keep only the hand-shake going
         if (!aborted) {
+            const long long m0 = hi * HALF;
+            // ---- can this half take the fast path? ------------------------------------------
+            bool fast = false;
+            double e_mine = 0.0;             // lanes 0-7: deviation of t from the uniform grid
+            if (fast_allowed && hi >= 1 && m0 + HALF <= N) {
+                if (!tab_ok) {
+                    if (cooldown > 0) {
+                        --cooldown;
+                    } else {
+                        // (re)build the tables for the cadence seen at the start of this half
+                        dtT = __shfl_sync(0xffffffffu, cur, 0) - t_prev;
+                        const double cdt = ps.cmax * dtT;
+                        const double kk = (cdt > 0.0) ? floor(RENORM_LIMIT / cdt) : 1.0e9;
+                        K = (int)fmin(fmax(kk, 1.0), (double)RENORM_STEPS);
 #pragma unroll 1
-            for (int s = 0; s < HALF; ++s) {
-                const long long m = hi * HALF + s;
-                const int slot = h * HALF + s;
-                const double tm = __shfl_sync(0xffffffffu, cur, s);
-                const double ym = __shfl_sync(0xffffffffu, cur, 8 + s);
-                const double dm = __shfl_sync(0xffffffffu, cur, 16 + s);
-                const bool valid = m < N;
-                const double dt = (m > 0) ? (tm - t_prev) : 0.0;
-                const bool rn = valid && m > 0 &&
-                                ((cmax * (tm - t_ref) > RENORM_LIMIT) || (m - m_ref >= RENORM_STEPS));
-                // decay over this step: cached factors, corrected to first order for a jittered
-                // cadence (|c eps| < 1e-8 for every term); exp only when the cadence changes
-                const double eps = dt - dt0;
-                const bool use_exp = valid && !(fabs(cmax * eps) < 1e-8);
+                        for (int i = 0; i <= HALF; ++i) {
+                            const double tau = (double)i * dtT;
 #pragma unroll
-                for (int k = 0; k < TPL; ++k) {
-                    double uc = 0.0, us = 0.0, vc = 0.0, vs = 0.0, r = 1.0;
-                    const int term = lane + 32 * k;
-                    if (valid && act[k]) {
-                        const double2 ab = sm.Kab[term], cdk = sm.Kcd[term];
-                        double p, pinv;
-                        if (use_exp) {
-                            p = exp(-cdk.x * dt);
-                            pinv = exp(cdk.x * dt);
-                            sm.Kp[term] = make_double2(p, pinv);
-                        } else {
-                            const double2 pc = sm.Kp[term];
-                            const double ce = cdk.x * eps;
-                            p = fma(-ce, pc.x, pc.x);
-                            pinv = fma(ce, pc.y, pc.y);
+                            for (int k = 0; k < TPL; ++k) {
+                                const int term = lane + 32 * k;
+                                const double2 cdk = sm.Kcd[term];
+                                double sn, cs;
+                                sincos_cw(cdk.y * tau, &sn, &cs);
+                                sm.TabT[i][term] = make_double2(cs, sn);
+                                sm.TabQ[i][term] = make_double2(exp(-cdk.x * tau), exp(cdk.x * tau));
+                            }
                         }
-                        double qn = q[k] * p, qi = qinv[k] * pinv;
-                        if (rn) { r = qn; qn = 1.0; qi = 1.0; }
-                        q[k] = qn; qinv[k] = qi;
-                        double sn, cs;
-                        sincos_cw(cdk.y * tm, &sn, &cs);
-                        uc = (ab.x * cs + ab.y * sn) * qn;
-                        us = (ab.x * sn - ab.y * cs) * qn;
-                        vc = cs * qi;
-                        vs = sn * qi;
-                    }
-                    if (term < JC_MAX) {
-                        sm.RU[slot][term] = make_double2(uc, us);
-                        sm.RV[slot][term] = make_double2(vc, vs);
-                        sm.Rr[slot][term] = r;
-                        if (MODE == MODE_FACTOR) sm.Rq[slot][term] = q[k];
+                        tab_ok = true;
+                        __syncwarp();
                     }
                 }
-                if (use_exp) dt0 = dt;
-                if (rn) { t_ref = tm; m_ref = m; }
-                if (valid) t_prev = tm;
-                if (m == 0) t_ref = tm;
-                if (lane == 0) {
-                    sm.Ra[slot] = (dm + ddiag) + sum_a;
-                    sm.Ry[slot] = ym;
-                    sm.Rflag[slot] = rn ? 1 : 0;
+                if (tab_ok) {
+                    e_mine = (cur - t_prev) - (double)((lane & 7) + 1) * dtT;
+                    const bool ok = (lane >= HALF) || (fabs(e_mine) * ps.wmax < 1.0e-8);
+                    fast = __all_sync(0xffffffffu, ok);
+                    if (!fast) { tab_ok = false; cooldown = 4; }
                 }
+            }
+            if (fast) {
+                // ---- fast half: 8 rows x 3 terms per lane, all independent -----------------
+                if (kb >= K) kb = K - 1;
+                {
+                    const int s = lane & 7;
+                    const int ks = (kb + s + 1) % K;
+                    const int rn = (ks == 0);
+                    const int pst = rn ? K : ks;            // steps since the previous frame change
+                    const bool inhalf = pst <= s;           // ... which happened at row s - pst of this half
+                    const double eprev = __shfl_sync(0xffffffffu, e_mine, inhalf ? s - pst : 0);
+                    const double ym = __shfl_sync(0xffffffffu, cur, 8 + s);
+                    const double dm = __shfl_sync(0xffffffffu, cur, 16 + s);
+                    if (lane < HALF) {
+                        // decay of the current frame at this row: table index / relative to the base
+                        // row or to the frame change inside this half; a row that changes the frame
+                        // starts at q = 1 and hands the decay of the old frame over as r
+                        const int ti = rn ? 0 : (inhalf ? pst : s + 1);
+                        const int useb = (!rn && !inhalf) ? 1 : 0;
+                        const int rti = inhalf ? pst : s + 1;
+                        sm.Ht[s] = cur;
+                        sm.Hde[s] = rn ? 0.0 : (inhalf ? e_mine - eprev : e_mine);
+                        sm.Hrde[s] = inhalf ? e_mine - eprev : e_mine;
+                        sm.Hcode[s] = ti | (useb << 4) | (rn << 5) | (rti << 8) | ((inhalf ? 0 : 1) << 12);
+                        const int slot = h * HALF + s;
+                        sm.Ra[slot] = (dm + ps.ddiag) + ps.sum_ad_a;
+                        sm.Ry[slot] = ym;
+                        sm.Rflag[slot] = rn;
+                    }
+                }
+                __syncwarp();
+                const bool resync = (hi & 7) == 7;
+#pragma unroll 1
+                for (int k = 0; k < TPL; ++k) {
+                    const int term = lane + 32 * k;
+                    const bool on = term < Jc;
+                    const double2 ab = sm.Kab[term], cdk = sm.Kcd[term];
+                    const double2 qb = sm.PBq[term], tb = sm.PBt[term];
+                    const double xbk = sm.PBx[term];
+                    double x_l = 0.0, cs_l = 1.0, sn_l = 0.0, q_l = 1.0, qi_l = 1.0;
+#pragma unroll 4
+                    for (int s = 0; s < HALF; ++s) {
+                        const double ts = sm.Ht[s], de = sm.Hde[s];
+                        const int code = sm.Hcode[s];
+                        const int ti = code & 15;
+                        const bool useb = (code & 16) != 0;
+                        const bool rn = (code & 32) != 0;
+                        const double tau = (double)(s + 1) * dtT;
+                        const int slot = h * HALF + s;
+                        const double2 T = sm.TabT[s + 1][term];
+                        const double2 Tq = sm.TabQ[ti][term];
+                        // phase: angle addition from the base row, first-order correction for the
+                        // difference between the rounded phase and the table angle
+                        const double x = cdk.y * ts;
+                        const double eps = (x - xbk) - cdk.y * tau;
+                        const double c1 = fma(tb.x, T.x, -(tb.y * T.y));
+                        const double s1 = fma(tb.y, T.x, tb.x * T.y);
+                        const double cs = fma(-eps, s1, c1);
+                        const double sn = fma(eps, c1, s1);
+                        // decay since the last frame change, first-order jitter correction
+                        const double ce = cdk.x * de;
+                        double qn = useb ? qb.x * Tq.x : Tq.x;
+                        double qi = useb ? qb.y * Tq.y : Tq.y;
+                        qn = fma(-ce, qn, qn);
+                        qi = fma(ce, qi, qi);
+                        double r = 1.0;
+                        if (rn) {   // warp-uniform, rare
+                            const int rti = (code >> 8) & 15;
+                            const double rq = sm.TabQ[rti][term].x * (((code >> 12) & 1) ? qb.x : 1.0);
+                            r = fma(-(cdk.x * sm.Hrde[s]), rq, rq);
+                        }
+                        if (term < JC_MAX) {
+                            sm.RU[slot][term] = on ? make_double2((ab.x * cs + ab.y * sn) * qn,
+                                                                  (ab.x * sn - ab.y * cs) * qn)
+                                                   : make_double2(0.0, 0.0);
+                            sm.RV[slot][term] = on ? make_double2(cs * qi, sn * qi) : make_double2(0.0, 0.0);
+                            sm.Rr[slot][term] = on ? r : 1.0;
+                            if (MODE == MODE_FACTOR) sm.Rq[slot][term] = qn;
+                        }
+                        x_l = x; cs_l = cs; sn_l = sn; q_l = qn; qi_l = qi;
+                    }
+                    if (resync) sincos_cw(x_l, &sn_l, &cs_l);
+                    sm.PBq[term] = make_double2(q_l, qi_l);
+                    sm.PBt[term] = make_double2(cs_l, sn_l);
+                    sm.PBx[term] = x_l;
+                }
+                kb = (kb + HALF) % K;
+                t_prev = __shfl_sync(0xffffffffu, cur, HALF - 1);
+                ps.m_ref = m0 + HALF - 1 - kb;
+                ps.t_ref = t_prev - (double)kb * dtT;
+                __syncwarp();
+            } else {
+                // ---- exact half: one row at a time (first half, ragged or gappy cadences) ----
+                const double cmax = ps.cmax;
+                double dt0 = ps.dt0, t_ref = ps.t_ref;
+                long long m_ref = ps.m_ref;
+#pragma unroll 1
+                for (int s = 0; s < HALF; ++s) {
+                    const long long m = m0 + s;
+                    const int slot = h * HALF + s;
+                    const double tm = __shfl_sync(0xffffffffu, cur, s);
+                    const double ym = __shfl_sync(0xffffffffu, cur, 8 + s);
+                    const double dm = __shfl_sync(0xffffffffu, cur, 16 + s);
+                    const bool valid = m < N;
+                    const double dt = (m > 0) ? (tm - t_prev) : 0.0;
+                    const bool rn = valid && m > 0 &&
+                                    ((cmax * (tm - t_ref) > RENORM_LIMIT) || (m - m_ref >= RENORM_STEPS));
+                    // decay over this step: cached factors, corrected to first order for a jittered
+                    // cadence (|c eps| < 1e-8 for every term); exp only when the cadence changes
+                    const double eps = dt - dt0;
+                    const bool use_exp = valid && !(fabs(cmax * eps) < 1e-8);
+#pragma unroll
+                    for (int k = 0; k < TPL; ++k) {
+                        double uc = 0.0, us = 0.0, vc = 0.0, vs = 0.0, r = 1.0, qk = 1.0;
+                        const int term = lane + 32 * k;
+                        if (valid && act[k]) {
+                            const double2 ab = sm.Kab[term], cdk = sm.Kcd[term];
+                            double p, pinv;
+                            if (use_exp) {
+                                p = exp(-cdk.x * dt);
+                                pinv = exp(cdk.x * dt);
+                                sm.Kp[term] = make_double2(p, pinv);
+                            } else {
+                                const double2 pc = sm.Kp[term];
+                                const double ce = cdk.x * eps;
+                                p = fma(-ce, pc.x, pc.x);
+                                pinv = fma(ce, pc.y, pc.y);
+                            }
+                            const double2 qo = sm.PBq[term];
+                            double qn = qo.x * p, qi = qo.y * pinv;
+                            if (rn) { r = qn; qn = 1.0; qi = 1.0; }
+                            qk = qn;
+                            double sn, cs;
+                            const double x = cdk.y * tm;
+                            sincos_cw(x, &sn, &cs);
+                            sm.PBq[term] = make_double2(qn, qi);
+                            sm.PBt[term] = make_double2(cs, sn);
+                            sm.PBx[term] = x;
+                            uc = (ab.x * cs + ab.y * sn) * qn;
+                            us = (ab.x * sn - ab.y * cs) * qn;
+                            vc = cs * qi;
+                            vs = sn * qi;
+                        }
+                        if (term < JC_MAX) {
+                            sm.RU[slot][term] = make_double2(uc, us);
+                            sm.RV[slot][term] = make_double2(vc, vs);
+                            sm.Rr[slot][term] = r;
+                            if (MODE == MODE_FACTOR) sm.Rq[slot][term] = qk;
+                        }
+                    }
+                    if (use_exp) dt0 = dt;
+                    if (rn) { t_ref = tm; m_ref = m; }
+                    if (valid) { t_prev = tm; kb = (int)(m - m_ref); }
+                    if (m == 0) t_ref = tm;
+                    if (lane == 0) {
+                        sm.Ra[slot] = (dm + ps.ddiag) + ps.sum_ad_a;
+                        sm.Ry[slot] = ym;
+                        sm.Rflag[slot] = rn ? 1 : 0;
+                    }
+                }
+                __syncwarp();
+                ps.dt0 = dt0; ps.t_ref = t_ref; ps.m_ref = m_ref;
+                __syncwarp();
             }
         }
         bar_arrive(BAR_FULL + h, N_RING);
