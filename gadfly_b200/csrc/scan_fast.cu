@@ -632,10 +632,10 @@ __device__ __forceinline__ double fast_rcp(double d)
     return x;
 }
 
-// Sum (a, b) over the three chain warps.  The first butterfly stage transposes: afterwards the
-// low half-warp carries a and the high half-warp b, so four more stages finish both.
-template <int PAR>
-__device__ __forceinline__ void chain_reduce2(FastSmem &sm, int hw, int lane, double &a, double &b)
+// Sum (a, b) over the three chain warps, in two parts so that independent work can be placed
+// between them.  The first butterfly stage transposes: afterwards the low half-warp carries a and
+// the high half-warp b, so four more stages finish both.
+__device__ __forceinline__ double chain_reduce2_warp(int lane, double a, double b)
 {
     const bool hi = (lane & 16) != 0;
     const double send = hi ? a : b, keep = hi ? b : a;
@@ -644,6 +644,11 @@ __device__ __forceinline__ void chain_reduce2(FastSmem &sm, int hw, int lane, do
     v += shfl_xor_d(v, 4);
     v += shfl_xor_d(v, 2);
     v += shfl_xor_d(v, 1);
+    return v;
+}
+template <int PAR>
+__device__ __forceinline__ void chain_reduce2_cta(FastSmem &sm, int hw, int lane, double v, double &a, double &b)
+{
     if ((lane & 15) == 0) reinterpret_cast<double *>(&sm.red2[PAR][hw])[lane >> 4] = v;
     bar_sync(BAR_CH, CH_THREADS);
     const double2 v0 = sm.red2[PAR][0], v1 = sm.red2[PAR][1], v2 = sm.red2[PAR][2];
@@ -651,11 +656,19 @@ __device__ __forceinline__ void chain_reduce2(FastSmem &sm, int hw, int lane, do
     b = (v0.y + v1.y) + v2.y;
 }
 
+// State the chain carries from step to step.  The serial path of the recurrence is kept as short
+// as possible: with t~_n = d_n w~_n = v~_n - h_n (no division) and tau_{n+1} = u~_{n+1} . t~_n,
+//   alpha_{n+1} = tau_{n+1} / d_n,   h_{n+1} = g_{n+1} + alpha_{n+1} t~_n,
+//   d_{n+1} = a_{n+1} - (u~ S~ u~^T + alpha_{n+1} tau_{n+1}),
+// so the reciprocal of the pivot runs beside the reduction of tau instead of in front of it.  The
+// forward substitution (F, gamma, z) lags one step behind and shares the reduction.
 struct ChainState {
-    double wc, ws;          // w~_{n-1}, in the frame of step n
-    double Fc, Fs;          // F~_n of this term, frame of step n
-    double alpha, gamma;    // u~_n . w~_{n-1},  u~_n . F~_n
-    double kappa;           // d_{n-1} alpha_n
+    double tc, ts;          // t~_{n-1} = d_{n-1} w~_{n-1}, in the frame of step n
+    double wc, ws;          // w~_{n-1}, frame of step n
+    double Fc, Fs;          // F~_{n-1}, frame of step n - 1
+    double alpha, tau;      // u~_n . w~_{n-1},  u~_n . t~_{n-1}
+    double rd;              // 1 / d_{n-1}
+    double zp;              // y_{n-1} (log-likelihood) or sqrt(d_{n-1}) n_{n-1} (sampling)
     double logdet, prod, quad;
 };
 
@@ -665,15 +678,47 @@ struct ChainConst {
     long long n0;
 };
 
+// Forward-substitution update for row m = n - 1 once gamma_m is known; returns the partial
+// product of gamma_n.  u0 = u~_n, r0 = frame change factor of row n.
+template <int MODE>
+__device__ __forceinline__ double solver_update(const ScanArgs &A, ChainState &st, const ChainConst &c,
+                                                const int m, const double gamma_m, const double2 u0,
+                                                const double r0)
+{
+    if (MODE == MODE_FACTOR) return 0.0;
+    double zp;
+    if (MODE == MODE_LOGLIKE) {
+        zp = st.zp - gamma_m;
+        st.quad = fma(zp * zp, st.rd, st.quad);
+    } else {
+        zp = st.zp;
+        if (c.ht == 0) A.out_x[c.n0 + m] = zp + gamma_m;
+    }
+    st.Fc = fma(st.wc, zp, st.Fc * r0);     // F~_n, frame of step n
+    st.Fs = fma(st.ws, zp, st.Fs * r0);
+    return c.act ? fma(u0.x, st.Fc, u0.y * st.Fs) : 0.0;
+}
+
 // One time step of the chain.  Returns false when the pivot is not positive.
 template <int MODE, int PAR>
 __device__ __forceinline__ bool chain_step(FastSmem &sm, const ScanArgs &A, ChainState &st,
-                                           const ChainConst &c, const int n)
+                                           const ChainConst &c, const int n, double &gamma_prev)
 {
     const int s0 = n & (RR - 1), s1 = (n + 1) & (RR - 1), s2 = (n + 2) & (RR - 1);
     const int tix = c.tix;
+    // ---- before the matrix results are needed: ring reads, forward substitution of row n - 1 ---
+    const double2 u0 = sm.RU[s0][tix];
+    const double r0 = sm.Rr[s0][tix];
+    const double2 vn = sm.RV[s0][tix];
+    const double ra = sm.Ra[s0], yn = sm.Ry[s0];
+    const double r1 = sm.Rr[s1][tix];
+    const double2 u1 = sm.RU[s1][tix];
+    const double2 u2 = sm.RU[s2][tix];
+    const double r2 = sm.Rr[s2][tix];
+    double gpart = 0.0;
+    if (n > 0) gpart = solver_update<MODE>(A, st, c, n - 1, gamma_prev, u0, r0);
+
     bar_sync(BAR_PART + PAR, N_OPS);
-    // everything this step reads, issued up front
     double2 v[NSLOT];
     {
         const double2 *Pp = reinterpret_cast<const double2 *>(&sm.P[PAR][0][0]) + tix;
@@ -682,33 +727,31 @@ __device__ __forceinline__ bool chain_step(FastSmem &sm, const ScanArgs &A, Chai
     }
     const double2 *Q2 = reinterpret_cast<const double2 *>(&sm.QF[PAR][0]);
     const double2 q0 = Q2[0], q1 = Q2[1], q2 = Q2[2], q3 = Q2[3];
-    const double2 vn = sm.RV[s0][tix];
-    const double ra = sm.Ra[s0], yn = sm.Ry[s0];
-    const double r1 = sm.Rr[s1][tix];
-    const double2 u1 = sm.RU[s1][tix];
-    const double2 u2 = sm.RU[s2][tix];
-    const double r2 = sm.Rr[s2][tix];
 
-    // pivot: d_n = a_n - (u~ S~(n-1) u~^T + d_{n-1} alpha_n^2)
-    const double qf = ((q0.x + q0.y) + (q1.x + q1.y)) + ((q2.x + q2.y) + (q3.x + q3.y));
-    const double dn = ra - fma(st.kappa, st.alpha, qf);
-    if (!(dn > 0.0)) return false;
-    const double rd = fast_rcp(dn);
     // g_n: unused slots hold zeros, so the sum always runs over all of them
     static_assert(NSLOT == 12, "summation tree below is written for 12 slots");
     const double gc = (((v[0].x + v[1].x) + (v[2].x + v[3].x)) + ((v[4].x + v[5].x) + (v[6].x + v[7].x))) +
                       ((v[8].x + v[9].x) + (v[10].x + v[11].x));
     const double gs = (((v[0].y + v[1].y) + (v[2].y + v[3].y)) + ((v[4].y + v[5].y) + (v[6].y + v[7].y))) +
                       ((v[8].y + v[9].y) + (v[10].y + v[11].y));
-    const double hc = fma(st.kappa, st.wc, gc), hs = fma(st.kappa, st.ws, gs);
-    const double tc = vn.x - hc, ts = vn.y - hs;            // d_n w~_n, frame of step n
-    const double wcn = tc * rd, wsn = ts * rd;              // w~_n
-    const double wc1 = wcn * r1, ws1 = wsn * r1;            // frame of step n + 1
+    // t~_n = v~_n - (g_n + alpha_n t~_{n-1}), then into the frame of step n + 1
+    const double tc = vn.x - fma(st.alpha, st.tc, gc), ts = vn.y - fma(st.alpha, st.ts, gs);
+    const double tc1 = tc * r1, ts1 = ts * r1;
+    // the serial path: tau_{n+1} = u~_{n+1} . t~_n (with gamma_n riding along)
+    const double tpart = c.act ? fma(u1.x, tc1, u1.y * ts1) : 0.0;
+    const double red = chain_reduce2_warp(c.lane, tpart, gpart);
+
+    // pivot, beside the reduction: d_n = a_n - (u~ S~(n-1) u~^T + alpha_n tau_n)
+    const double qf = ((q0.x + q0.y) + (q1.x + q1.y)) + ((q2.x + q2.y) + (q3.x + q3.y));
+    const double dn = ra - fma(st.alpha, st.tau, qf);
+    if (!(dn > 0.0)) return false;
+    const double rd = fast_rcp(dn);
+    const double wc1 = tc1 * rd, ws1 = ts1 * rd;            // w~_n, frame of step n + 1
     // operands of matrix phase n + 2: row n + 2 and the rank-1 term of step n
     if (n + 2 < c.N) {
         if (c.act) {
-            sm.A[PAR][c.ke][c.kb] = make_double2(u2.x, tc * r1);
-            sm.A[PAR][c.ke + 1][c.kb] = make_double2(u2.y, ts * r1);
+            sm.A[PAR][c.ke][c.kb] = make_double2(u2.x, tc1);
+            sm.A[PAR][c.ke + 1][c.kb] = make_double2(u2.y, ts1);
             sm.C[PAR][c.ke][c.kb] = make_double2(u2.x, wc1);
             sm.C[PAR][c.ke + 1][c.kb] = make_double2(u2.y, ws1);
             *reinterpret_cast<double2 *>(&sm.R[PAR][c.k0]) = make_double2(r2, r2);
@@ -716,36 +759,24 @@ __device__ __forceinline__ bool chain_step(FastSmem &sm, const ScanArgs &A, Chai
         if (c.ht == 0) sm.renorm[PAR] = sm.Rflag[s2];
         bar_arrive(BAR_OPS + PAR, N_OPS);
     }
-    // ---- off the critical path ------------------------------------------------------------
-    if (MODE == MODE_FACTOR && A.out_W && c.act) {
-        const double qn = sm.Rq[s0][tix];
-        double *Wn = A.out_W + A.w_off[c.b] + (long long)n * c.J;
-        Wn[c.term] = wcn * qn;
-        Wn[c.Jc + c.term] = wsn * qn;
-    }
-    double zp;
-    if (MODE == MODE_LOGLIKE) {
-        const double zn = yn - st.gamma;
-        st.quad = fma(zn * zn, rd, st.quad);
-        zp = zn;
-    } else if (MODE == MODE_SAMPLE) {
-        zp = yn * sqrt(dn);
-        if (c.ht == 0) A.out_x[c.n0 + n] = zp + st.gamma;
-    } else {
-        zp = 0.0;
+    // ---- off the matrix' critical path --------------------------------------------------------
+    double tau, gamma;
+    chain_reduce2_cta<PAR>(sm, c.hw, c.lane, red, tau, gamma);
+    if (MODE == MODE_FACTOR) {
+        if (A.out_W && c.act) {
+            const double qn = sm.Rq[s0][tix];
+            double *Wn = A.out_W + A.w_off[c.b] + (long long)n * c.J;
+            Wn[c.term] = (tc * rd) * qn;
+            Wn[c.Jc + c.term] = (ts * rd) * qn;
+        }
         if (c.ht == 0) A.out_x[c.n0 + n] = dn;
     }
+    st.zp = (MODE == MODE_SAMPLE) ? yn * sqrt(dn) : yn;
     st.prod *= dn;
     if ((n & 7) == 7) { if (c.ht == 0) st.logdet += log(st.prod); st.prod = 1.0; }
-    st.Fc = fma(wcn, zp, st.Fc) * r1;                       // F~_{n+1}, frame of step n + 1
-    st.Fs = fma(wsn, zp, st.Fs) * r1;
-    st.wc = wc1; st.ws = ws1;
-    if (n + 1 < c.N) {
-        double alpha = c.act ? fma(u1.x, wc1, u1.y * ws1) : 0.0;
-        double gamma = c.act ? fma(u1.x, st.Fc, u1.y * st.Fs) : 0.0;
-        chain_reduce2<PAR>(sm, c.hw, c.lane, alpha, gamma);
-        st.alpha = alpha; st.gamma = gamma; st.kappa = dn * alpha;
-    }
+    st.tc = tc1; st.ts = ts1; st.wc = wc1; st.ws = ws1;
+    st.tau = tau; st.alpha = tau * rd; st.rd = rd;
+    gamma_prev = gamma;
     return true;
 }
 
@@ -783,8 +814,10 @@ __device__ __forceinline__ void chain_loop(FastSmem &sm, const ScanArgs &A, cons
     if (N > 1) bar_arrive(BAR_OPS + 1, N_OPS);
 
     ChainState st;
-    st.wc = st.ws = st.Fc = st.Fs = st.alpha = st.gamma = st.kappa = 0.0;
+    st.tc = st.ts = st.wc = st.ws = st.Fc = st.Fs = st.alpha = st.tau = 0.0;
+    st.rd = 0.0; st.zp = 0.0;
     st.logdet = 0.0; st.prod = 1.0; st.quad = 0.0;
+    double gamma_prev = 0.0;
     int32_t fail = 0;
     bool drain = false;
 
@@ -793,8 +826,8 @@ __device__ __forceinline__ void chain_loop(FastSmem &sm, const ScanArgs &A, cons
         if (((n + 2) & (HALF - 1)) == 0 && (n + 2) / HALF < nh)
             bar_sync(BAR_FULL + (((n + 2) / HALF) & 1), N_RING);
         if (!drain) {
-            const bool ok = (n & 1) ? chain_step<MODE, 1>(sm, A, st, c, n)
-                                    : chain_step<MODE, 0>(sm, A, st, c, n);
+            const bool ok = (n & 1) ? chain_step<MODE, 1>(sm, A, st, c, n, gamma_prev)
+                                    : chain_step<MODE, 0>(sm, A, st, c, n, gamma_prev);
             if (!ok) {
                 // not positive definite: stop the matrix warps at phase n + 2, absorb the
                 // arrival of phase n + 1 (already released), then only keep the ring
@@ -810,6 +843,15 @@ __device__ __forceinline__ void chain_loop(FastSmem &sm, const ScanArgs &A, cons
         // ring hand-over: row n is dead now
         if ((n & (HALF - 1)) == HALF - 1 && n / HALF + 2 < nh)
             bar_arrive(BAR_EMPTY + ((n / HALF) & 1), N_RING);
+    }
+    // forward substitution of the last row
+    if (!drain && MODE != MODE_FACTOR) {
+        if (MODE == MODE_LOGLIKE) {
+            const double z = st.zp - gamma_prev;
+            st.quad = fma(z * z, st.rd, st.quad);
+        } else if (ht == 0) {
+            A.out_x[c.n0 + N - 1] = st.zp + gamma_prev;
+        }
     }
     if (ht == 0) {
         if (st.prod != 1.0) st.logdet += log(st.prod);
