@@ -49,6 +49,11 @@ constexpr int TPW = 30;              // complex terms per chain warp (3 x 30 = 9
 constexpr int JC_MAX = JP_MAX / 2;   // 88
 constexpr int NSB_MAX = NB_MAX / 2;  // 16 x 16 super-blocks per side
 constexpr int NSLOT = NSB_MAX + 1;   // partial-sum slots per column
+// A slot of partial sums is JP_MAX doubles, stored as 16-byte chunks (one complex term: cos and
+// sin column).  Chunk c of slot s lives at index c ^ ((s + (c >> 3)) & 1): neighbouring 2x2 groups
+// of a warp then hit complementary banks and the 16-byte stores run conflict-free.
+constexpr int CTL_RENORM = 1, CTL_STOP = 2;
+__host__ __device__ constexpr int pchunk(int chunk, int slot) { return chunk ^ ((slot + (chunk >> 3)) & 1); }
 constexpr int RR = 16;               // row ring depth (two halves)
 constexpr int HALF = 8;
 constexpr int REG_MAT = 208;
@@ -111,7 +116,7 @@ struct FastSmem {
     double Ht[HALF], Hde[HALF], Hrde[HALF];
     int Hcode[HALF];
     ProdScalars ps;
-    int renorm[2];
+    int ctl[2];                     // per matrix phase parity: CTL_RENORM / CTL_STOP
     int stop;                       // first matrix phase that must not run
     int next;
 };
@@ -195,105 +200,192 @@ __device__ __forceinline__ TileMap make_tile_map(int mt, int nsb)
     return m;
 }
 
-template <int PAR>
-__device__ __forceinline__ void matrix_step(FastSmem &sm, double (&S)[TILE][TILE], const TileMap &tm,
-                                            const double qw, const int lane, const int warp)
-{
-    const int bi = tm.bi, bj = tm.bj;
-    double uj[TILE], wj[TILE];
-#pragma unroll
-    for (int e = 0; e < TILE; ++e) {
-        const double2 c = sm.C[PAR][e][bj];
-        uj[e] = c.x; wj[e] = c.y;
-    }
-    if (sm.renorm[PAR]) {
-        // frame change: S~ <- r r^T o (S~ + d w~ w~^T); the rank-1 term is consumed here
-#pragma unroll
-        for (int i = 0; i < TILE; ++i) {
-            const double dwi = sm.A[PAR][i][bi].y;
-            const double rgi = sm.R[PAR][bi * TILE + i];
-#pragma unroll
-            for (int j = 0; j < TILE; ++j) {
-                const double rgj = sm.R[PAR][bj * TILE + j];
-                S[i][j] = (rgi * fma(dwi, wj[j], S[i][j])) * rgj;
-            }
-        }
-#pragma unroll
-        for (int e = 0; e < TILE; ++e) wj[e] = 0.0;
-    }
+// Per-thread constants of a matrix thread.  (All lanes of a warp read the operands in the same
+// order: letting each lane of a 2x2 group walk its rows / columns in its own order would save the
+// selects of the exchange but doubles the shared-memory wavefronts of the operand loads -- measured.)
+struct MatConst {
+    const double2 *a_lo, *a_hi, *c_lo, *c_hi;  // in A[0] / C[0]: operands of local rows / columns 0 and 4
+    uint32_t pr0, pc0;                // shared-space addresses in P[0] of the first row / column chunk stored
+    int geom;                         // bi | bj << 8 | mr << 16 | mc << 20 | kind << 24 (rare paths)
+    double qw;
+};
+__device__ __forceinline__ int geom_bi(int g) { return g & 255; }
+__device__ __forceinline__ int geom_bj(int g) { return (g >> 8) & 255; }
+__device__ __forceinline__ int geom_mr(int g) { return (g >> 16) & 15; }
+__device__ __forceinline__ int geom_mc(int g) { return (g >> 20) & 15; }
+__device__ __forceinline__ int geom_kind(int g) { return g >> 24; }
 
-    // rank-1 update fused with the two partial matrix-vector products; two rows at a time so
-    // that the two row accumulators and the eight column accumulators are independent chains
-    double colp[TILE], rowp[TILE];
+__device__ __forceinline__ MatConst make_mat_const(const FastSmem &sm, const TileMap &tm)
+{
+    MatConst m;
+    // mr / mc: first of the four rows / columns whose sums this lane keeps after the exchange
+    const int mr = (tm.kind == 0) ? 4 * tm.cj : 0;
+    const int mc = (tm.kind == 0) ? 4 * tm.ri : 0;
+    m.geom = tm.bi | (tm.bj << 8) | (mr << 16) | (mc << 20) | (tm.kind << 24);
+    m.a_lo = &sm.A[0][0][tm.bi];
+    m.a_hi = &sm.A[0][4][tm.bi];
+    m.c_lo = &sm.C[0][0][tm.bj];
+    m.c_hi = &sm.C[0][4][tm.bj];
+    // first stored chunk: actual rows mr.. of block bi (kind 0: two chunks, else four); the k-th
+    // chunk is at byte address pr0 ^ (16 k) thanks to the alignment of the groups of four chunks
+    const double2 *P2 = reinterpret_cast<const double2 *>(&sm.P[0][0][0]);
+    const int cr = 4 * tm.bi + mr / 2, cc = 4 * tm.bj + mc / 2;
+    m.pr0 = (uint32_t)__cvta_generic_to_shared(P2 + tm.slot_row * (JP_MAX / 2) + pchunk(cr, tm.slot_row));
+    m.pc0 = (uint32_t)__cvta_generic_to_shared(P2 + tm.slot_col * (JP_MAX / 2) + pchunk(cc, tm.slot_col));
+    // weight of this tile in the quadratic form: off-diagonal tiles stand for their mirror too
+    m.qw = (tm.kind == 3) ? 0.0 : ((tm.bi == tm.bj) ? 1.0 : 2.0);
+    return m;
+}
+
+// 16-byte shared-memory accesses at a per-thread base address plus a compile-time offset (kept as
+// one register + immediate, so that no address arithmetic is hoisted into registers)
+template <int OFF>
+__device__ __forceinline__ double2 lds_v2(const uint32_t addr)
+{
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v.x), "=d"(v.y) : "r"(addr), "n"(OFF) : "memory");
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ void sts_v2(const uint32_t addr, const double x, const double y)
+{
+    asm volatile("st.shared.v2.f64 [%0+%1], {%2, %3};" ::"r"(addr), "n"(OFF), "d"(x), "d"(y) : "memory");
+}
+constexpr int P_PAR_BYTES = (int)sizeof(double) * NSLOT * JP_MAX;       // P[1] - P[0]
+template <int PAR, int I>
+__device__ __forceinline__ double2 mat_row_op(const MatConst &mc)
+{
+    return ((I < 4) ? mc.a_lo : mc.a_hi)[PAR * TILE * NB_MAX + (I & 3) * NB_MAX];
+}
+template <int PAR, int J>
+__device__ __forceinline__ double2 mat_col_op(const MatConst &mc)
+{
+    return ((J < 4) ? mc.c_lo : mc.c_hi)[PAR * TILE * NB_MAX + (J & 3) * NB_MAX];
+}
+
+template <int I>
+__device__ __forceinline__ void matrix_row_pair(const double2 a0, const double2 a1, double (&S)[TILE][TILE],
+                                                const double (&uj)[TILE], const double (&wj)[TILE],
+                                                double (&rowp)[TILE], double (&colp)[TILE])
+{
+    double rp0 = 0.0, rp1 = 0.0;
 #pragma unroll
-    for (int e = 0; e < TILE; ++e) colp[e] = 0.0;
+    for (int j = 0; j < TILE; ++j) {
+        const double T0 = fma(a0.y, wj[j], S[I][j]);
+        const double T1 = fma(a1.y, wj[j], S[I + 1][j]);
+        S[I][j] = T0; S[I + 1][j] = T1;
+        colp[j] = fma(a0.x, T0, colp[j]);
+        rp0 = fma(T0, uj[j], rp0);
+        colp[j] = fma(a1.x, T1, colp[j]);
+        rp1 = fma(T1, uj[j], rp1);
+    }
+    rowp[I] = rp0; rowp[I + 1] = rp1;
+}
+
+// frame change: S~ <- r r^T o (S~ + d w~ w~^T); the rank-1 term is consumed here (rare)
+template <int PAR>
+__device__ __forceinline__ void matrix_renorm(FastSmem &sm, double (&S)[TILE][TILE], const int geom,
+                                              double (&wj)[TILE])
+{
+    const int bi = geom_bi(geom), bj = geom_bj(geom);
 #pragma unroll
-    for (int i = 0; i < TILE; i += 2) {
-        const double2 a0 = sm.A[PAR][i][bi], a1 = sm.A[PAR][i + 1][bi];
-        double rp0 = 0.0, rp1 = 0.0;
+    for (int i = 0; i < TILE; ++i) {
+        const double dwi = sm.A[PAR][i][bi].y;
+        const double rgi = sm.R[PAR][bi * TILE + i];
 #pragma unroll
         for (int j = 0; j < TILE; ++j) {
-            const double T0 = fma(a0.y, wj[j], S[i][j]);
-            const double T1 = fma(a1.y, wj[j], S[i + 1][j]);
-            S[i][j] = T0; S[i + 1][j] = T1;
-            colp[j] = fma(a0.x, T0, colp[j]);
-            rp0 = fma(T0, uj[j], rp0);
-            colp[j] = fma(a1.x, T1, colp[j]);
-            rp1 = fma(T1, uj[j], rp1);
+            const double rgj = sm.R[PAR][bj * TILE + j];
+            S[i][j] = (rgi * fma(dwi, wj[j], S[i][j])) * rgj;
         }
-        rowp[i] = rp0; rowp[i + 1] = rp1;
     }
+#pragma unroll
+    for (int e = 0; e < TILE; ++e) wj[e] = 0.0;
+}
+
+// One phase of a matrix thread: wait for the operands, (renormalisation,) the arithmetic, the
+// exchange inside the 2x2 group, the warp reduction of the quadratic form, stores and hand-over.
+template <int PAR>
+__device__ __forceinline__ int matrix_phase(FastSmem &sm, double (&S)[TILE][TILE], const MatConst &mc,
+                                            const int lane, const int warp)
+{
+    bar_sync(BAR_OPS + PAR, N_OPS);
+    double uj[TILE], wj[TILE];
+    {
+        double2 c;
+        c = mat_col_op<PAR, 0>(mc); uj[0] = c.x; wj[0] = c.y;
+        c = mat_col_op<PAR, 1>(mc); uj[1] = c.x; wj[1] = c.y;
+        c = mat_col_op<PAR, 2>(mc); uj[2] = c.x; wj[2] = c.y;
+        c = mat_col_op<PAR, 3>(mc); uj[3] = c.x; wj[3] = c.y;
+        c = mat_col_op<PAR, 4>(mc); uj[4] = c.x; wj[4] = c.y;
+        c = mat_col_op<PAR, 5>(mc); uj[5] = c.x; wj[5] = c.y;
+        c = mat_col_op<PAR, 6>(mc); uj[6] = c.x; wj[6] = c.y;
+        c = mat_col_op<PAR, 7>(mc); uj[7] = c.x; wj[7] = c.y;
+    }
+    const int ctl = sm.ctl[PAR];
+    if (ctl) {
+        if (ctl & CTL_STOP) return ctl;
+        matrix_renorm<PAR>(sm, S, mc.geom, wj);
+    }
+
+    double rowp[TILE], colp[TILE];
+#pragma unroll
+    for (int e = 0; e < TILE; ++e) colp[e] = 0.0;
+    // two rows at a time so that the two row accumulators and the eight column accumulators are
+    // independent chains
+    matrix_row_pair<0>(mat_row_op<PAR, 0>(mc), mat_row_op<PAR, 1>(mc), S, uj, wj, rowp, colp);
+    matrix_row_pair<2>(mat_row_op<PAR, 2>(mc), mat_row_op<PAR, 3>(mc), S, uj, wj, rowp, colp);
+    matrix_row_pair<4>(mat_row_op<PAR, 4>(mc), mat_row_op<PAR, 5>(mc), S, uj, wj, rowp, colp);
+    matrix_row_pair<6>(mat_row_op<PAR, 6>(mc), mat_row_op<PAR, 7>(mc), S, uj, wj, rowp, colp);
 
     // quadratic form u~ S~ u~^T: this tile's share, reduced over the warp
     double qf0 = colp[0] * uj[0], qf1 = colp[1] * uj[1];
 #pragma unroll
     for (int j = 2; j < TILE; j += 2) { qf0 = fma(colp[j], uj[j], qf0); qf1 = fma(colp[j + 1], uj[j + 1], qf1); }
-    double qf = (qf0 + qf1) * qw;
+    double qf = (qf0 + qf1) * mc.qw;
 
-    // 2x2 group: combine the two tiles of a block row (lane ^ 1) and of a block column
-    // (lane ^ 2); each lane keeps four of the eight sums
+    // 2x2 group: combine the two tiles of a block row (lane ^ 1) and of a block column (lane ^ 2)
+    // (each lane keeps four of the eight sums: rows 4 cj.., columns 4 ri..)
+    const bool hr = geom_mr(mc.geom) != 0, hc = geom_mc(mc.geom) != 0;
     double rs[4], cs[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        const double send_r = tm.cj ? rowp[q] : rowp[4 + q];
-        const double keep_r = tm.cj ? rowp[4 + q] : rowp[q];
+        const double send_r = hr ? rowp[q] : rowp[4 + q];
+        const double keep_r = hr ? rowp[4 + q] : rowp[q];
         rs[q] = keep_r + shfl_xor_d(send_r, 1);
-        const double send_c = tm.ri ? colp[q] : colp[4 + q];
-        const double keep_c = tm.ri ? colp[4 + q] : colp[q];
+        const double send_c = hc ? colp[q] : colp[4 + q];
+        const double keep_c = hc ? colp[4 + q] : colp[q];
         cs[q] = keep_c + shfl_xor_d(send_c, 2);
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) qf += shfl_xor_d(qf, off);
     if (lane == 0) sm.QF[PAR][warp] = qf;
 
-    if (tm.kind == 0) {
-        double *pr = &sm.P[PAR][tm.slot_row][bi * TILE + tm.cj * 4];
-        double *pc = &sm.P[PAR][tm.slot_col][bj * TILE + tm.ri * 4];
-        *reinterpret_cast<double2 *>(pr) = make_double2(rs[0], rs[1]);
-        *reinterpret_cast<double2 *>(pr + 2) = make_double2(rs[2], rs[3]);
-        *reinterpret_cast<double2 *>(pc) = make_double2(cs[0], cs[1]);
-        *reinterpret_cast<double2 *>(pc + 2) = make_double2(cs[2], cs[3]);
-    } else if (tm.kind == 1) {
-        double *pc = &sm.P[PAR][tm.slot_col][bj * TILE];
+    const int kind = geom_kind(mc.geom);
+    if (kind == 0) {
+        sts_v2<PAR * P_PAR_BYTES>(mc.pr0, rs[0], rs[1]);
+        sts_v2<PAR * P_PAR_BYTES>(mc.pr0 ^ 16u, rs[2], rs[3]);
+        sts_v2<PAR * P_PAR_BYTES>(mc.pc0, cs[0], cs[1]);
+        sts_v2<PAR * P_PAR_BYTES>(mc.pc0 ^ 16u, cs[2], cs[3]);
+    } else if (kind == 1) {
+        // diagonal tile: its (symmetric) contribution is stored once
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<double2 *>(pc + 2 * q) = make_double2(colp[2 * q], colp[2 * q + 1]);
-    } else if (tm.kind == 2) {
-        double *pr = &sm.P[PAR][tm.slot_row][bi * TILE];
-        double *pc = &sm.P[PAR][tm.slot_col][bj * TILE];
+            sts_v2<PAR * P_PAR_BYTES>(mc.pc0 ^ (16u * q), colp[2 * q], colp[2 * q + 1]);
+    } else if (kind == 2) {
+        // off-diagonal tile of a diagonal super-block: both contributions, no partner lanes
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            *reinterpret_cast<double2 *>(pr + 2 * q) = make_double2(rowp[2 * q], rowp[2 * q + 1]);
-            *reinterpret_cast<double2 *>(pc + 2 * q) = make_double2(colp[2 * q], colp[2 * q + 1]);
+            sts_v2<PAR * P_PAR_BYTES>(mc.pr0 ^ (16u * q), rowp[2 * q], rowp[2 * q + 1]);
+            sts_v2<PAR * P_PAR_BYTES>(mc.pc0 ^ (16u * q), colp[2 * q], colp[2 * q + 1]);
         }
     }
+    bar_arrive(BAR_PART + PAR, N_OPS);
+    return ctl;
 }
 
 __device__ __forceinline__ void matrix_loop(FastSmem &sm, const int mt, const int nsb, const int N)
 {
-    const TileMap tm = make_tile_map(mt, nsb);
-    // weight of this tile in the quadratic form: off-diagonal tiles stand for their mirror too
-    const double qw = (tm.kind == 3) ? 0.0 : ((tm.bi == tm.bj) ? 1.0 : 2.0);
+    const MatConst mc = make_mat_const(sm, make_tile_map(mt, nsb));
     const int lane = mt & 31, warp = mt >> 5;
     double S[TILE][TILE];
 #pragma unroll
@@ -301,18 +393,11 @@ __device__ __forceinline__ void matrix_loop(FastSmem &sm, const int mt, const in
 #pragma unroll
         for (int j = 0; j < TILE; ++j) S[i][j] = 0.0;
 
-    const volatile int *stop = &sm.stop;
-    int n = 0;
-    for (;;) {
-        bar_sync(BAR_OPS + 0, N_OPS);
-        if (n >= *stop) break;
-        matrix_step<0>(sm, S, tm, qw, lane, warp);
-        bar_arrive(BAR_PART + 0, N_OPS);
+    // the chain stops the matrix warps only at a phase it has not released yet
+    for (int n = 0;;) {
+        if (matrix_phase<0>(sm, S, mc, lane, warp) & CTL_STOP) break;
         if (++n >= N) break;
-        bar_sync(BAR_OPS + 1, N_OPS);
-        if (n >= *stop) break;
-        matrix_step<1>(sm, S, tm, qw, lane, warp);
-        bar_arrive(BAR_PART + 1, N_OPS);
+        if (matrix_phase<1>(sm, S, mc, lane, warp) & CTL_STOP) break;
         if (++n >= N) break;
     }
 }
@@ -673,7 +758,7 @@ struct ChainState {
 };
 
 struct ChainConst {
-    int ht, hw, lane, term, tix, k0, kb, ke, Jc, J, N, b;
+    int ht, hw, lane, term, tix, tixA, tixB, k0, kb, ke, Jc, J, N, b;
     bool act;
     long long n0;
 };
@@ -719,17 +804,14 @@ __device__ __forceinline__ bool chain_step(FastSmem &sm, const ScanArgs &A, Chai
     if (n > 0) gpart = solver_update<MODE>(A, st, c, n - 1, gamma_prev, u0, r0);
 
     bar_sync(BAR_PART + PAR, N_OPS);
-    double2 v[NSLOT];
-    {
-        const double2 *Pp = reinterpret_cast<const double2 *>(&sm.P[PAR][0][0]) + tix;
-#pragma unroll
-        for (int s = 0; s < NSLOT; ++s) v[s] = Pp[s * (JP_MAX / 2)];
-    }
-    const double2 *Q2 = reinterpret_cast<const double2 *>(&sm.QF[PAR][0]);
-    const double2 q0 = Q2[0], q1 = Q2[1], q2 = Q2[2], q3 = Q2[3];
-
     // g_n: unused slots hold zeros, so the sum always runs over all of them
     static_assert(NSLOT == 12, "summation tree below is written for 12 slots");
+    double2 v[NSLOT];
+    {
+        const double2 *Pp = reinterpret_cast<const double2 *>(&sm.P[PAR][0][0]);
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) v[s] = Pp[s * (JP_MAX / 2) + ((s & 1) ? c.tixB : c.tixA)];
+    }
     const double gc = (((v[0].x + v[1].x) + (v[2].x + v[3].x)) + ((v[4].x + v[5].x) + (v[6].x + v[7].x))) +
                       ((v[8].x + v[9].x) + (v[10].x + v[11].x));
     const double gs = (((v[0].y + v[1].y) + (v[2].y + v[3].y)) + ((v[4].y + v[5].y) + (v[6].y + v[7].y))) +
@@ -742,6 +824,8 @@ __device__ __forceinline__ bool chain_step(FastSmem &sm, const ScanArgs &A, Chai
     const double red = chain_reduce2_warp(c.lane, tpart, gpart);
 
     // pivot, beside the reduction: d_n = a_n - (u~ S~(n-1) u~^T + alpha_n tau_n)
+    const double2 *Q2 = reinterpret_cast<const double2 *>(&sm.QF[PAR][0]);
+    const double2 q0 = Q2[0], q1 = Q2[1], q2 = Q2[2], q3 = Q2[3];
     const double qf = ((q0.x + q0.y) + (q1.x + q1.y)) + ((q2.x + q2.y) + (q3.x + q3.y));
     const double dn = ra - fma(st.alpha, st.tau, qf);
     if (!(dn > 0.0)) return false;
@@ -756,7 +840,7 @@ __device__ __forceinline__ bool chain_step(FastSmem &sm, const ScanArgs &A, Chai
             sm.C[PAR][c.ke + 1][c.kb] = make_double2(u2.y, ws1);
             *reinterpret_cast<double2 *>(&sm.R[PAR][c.k0]) = make_double2(r2, r2);
         }
-        if (c.ht == 0) sm.renorm[PAR] = sm.Rflag[s2];
+        if (c.ht == 0) sm.ctl[PAR] = sm.Rflag[s2] ? CTL_RENORM : 0;
         bar_arrive(BAR_OPS + PAR, N_OPS);
     }
     // ---- off the matrix' critical path --------------------------------------------------------
@@ -789,6 +873,7 @@ __device__ __forceinline__ void chain_loop(FastSmem &sm, const ScanArgs &A, cons
     c.term = c.hw * TPW + c.lane;
     c.act = (c.lane < TPW) && (c.term < Jc);
     c.tix = c.act ? c.term : 0;              // inactive lanes shadow term 0 and store nothing
+    c.tixA = pchunk(c.tix, 0); c.tixB = pchunk(c.tix, 1);   // chunk of this term in even / odd slots
     c.k0 = 2 * c.tix;                        // cos column; sin column is k0 + 1
     c.kb = c.k0 >> 3; c.ke = c.k0 & 7;       // both columns sit in block kb (ke is even)
     c.Jc = Jc; c.J = 2 * Jc; c.N = N; c.b = b;
@@ -809,7 +894,7 @@ __device__ __forceinline__ void chain_loop(FastSmem &sm, const ScanArgs &A, cons
         const double r1 = sm.Rr[1][tix];
         sm.R[1][c.k0] = r1; sm.R[1][c.k0 + 1] = r1;
     }
-    if (ht == 0) { sm.renorm[0] = 0; sm.renorm[1] = (N > 1) ? sm.Rflag[1] : 0; }
+    if (ht == 0) { sm.ctl[0] = 0; sm.ctl[1] = (N > 1 && sm.Rflag[1]) ? CTL_RENORM : 0; }
     bar_arrive(BAR_OPS + 0, N_OPS);
     if (N > 1) bar_arrive(BAR_OPS + 1, N_OPS);
 
@@ -834,7 +919,7 @@ __device__ __forceinline__ void chain_loop(FastSmem &sm, const ScanArgs &A, cons
                 // hand-shake with the producer going until the natural end
                 const int par = n & 1;
                 fail = n + 1;
-                if (ht == 0) sm.stop = n + 2;
+                if (ht == 0) { sm.stop = n + 2; sm.ctl[par] = CTL_STOP; }
                 if (n + 2 < N) bar_arrive(BAR_OPS + par, N_OPS);
                 if (n + 1 < N) bar_sync(BAR_PART + (par ^ 1), N_OPS);
                 drain = true;
