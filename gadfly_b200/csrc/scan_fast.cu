@@ -804,18 +804,22 @@ __device__ __forceinline__ bool chain_step(FastSmem &sm, const ScanArgs &A, Chai
     if (n > 0) gpart = solver_update<MODE>(A, st, c, n - 1, gamma_prev, u0, r0);
 
     bar_sync(BAR_PART + PAR, N_OPS);
-    // g_n: unused slots hold zeros, so the sum always runs over all of them
+    // g_n: unused slots hold zeros, so the sum always runs over all of them (two batches of six
+    // slots to keep the register footprint of the loads small)
     static_assert(NSLOT == 12, "summation tree below is written for 12 slots");
-    double2 v[NSLOT];
+    double gc, gs;
     {
         const double2 *Pp = reinterpret_cast<const double2 *>(&sm.P[PAR][0][0]);
+        double2 v[6];
 #pragma unroll
-        for (int s = 0; s < NSLOT; ++s) v[s] = Pp[s * (JP_MAX / 2) + ((s & 1) ? c.tixB : c.tixA)];
+        for (int s = 0; s < 6; ++s) v[s] = Pp[s * (JP_MAX / 2) + ((s & 1) ? c.tixB : c.tixA)];
+        const double gc0 = ((v[0].x + v[1].x) + (v[2].x + v[3].x)) + (v[4].x + v[5].x);
+        const double gs0 = ((v[0].y + v[1].y) + (v[2].y + v[3].y)) + (v[4].y + v[5].y);
+#pragma unroll
+        for (int s = 0; s < 6; ++s) v[s] = Pp[(s + 6) * (JP_MAX / 2) + ((s & 1) ? c.tixB : c.tixA)];
+        gc = gc0 + (((v[0].x + v[1].x) + (v[2].x + v[3].x)) + (v[4].x + v[5].x));
+        gs = gs0 + (((v[0].y + v[1].y) + (v[2].y + v[3].y)) + (v[4].y + v[5].y));
     }
-    const double gc = (((v[0].x + v[1].x) + (v[2].x + v[3].x)) + ((v[4].x + v[5].x) + (v[6].x + v[7].x))) +
-                      ((v[8].x + v[9].x) + (v[10].x + v[11].x));
-    const double gs = (((v[0].y + v[1].y) + (v[2].y + v[3].y)) + ((v[4].y + v[5].y) + (v[6].y + v[7].y))) +
-                      ((v[8].y + v[9].y) + (v[10].y + v[11].y));
     // t~_n = v~_n - (g_n + alpha_n t~_{n-1}), then into the frame of step n + 1
     const double tc = vn.x - fma(st.alpha, st.tc, gc), ts = vn.y - fma(st.alpha, st.ts, gs);
     const double tc1 = tc * r1, ts1 = ts * r1;
