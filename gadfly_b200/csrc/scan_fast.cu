@@ -48,6 +48,9 @@ constexpr int CH_THREADS = 96;
 constexpr int TPW = 30;              // complex terms per chain warp (3 x 30 = 90 >= 88)
 constexpr int JC_MAX = JP_MAX / 2;   // 88
 constexpr int NSB_MAX = NB_MAX / 2;  // 16 x 16 super-blocks per side
+// row pitch of the operand arrays A / C: 23 instead of 22 entries, so that the four 16-byte stores
+// of neighbouring chain lanes (same block, elements 0, 2, 4, 6) fall into different banks
+constexpr int NB_PAD = NB_MAX + 1;
 constexpr int NSLOT = NSB_MAX + 1;   // partial-sum slots per column
 // A slot of partial sums is JP_MAX doubles, stored as 16-byte chunks (one complex term: cos and
 // sin column).  Chunk c of slot s lives at index c ^ ((s + (c >> 3)) & 1): neighbouring 2x2 groups
@@ -86,8 +89,8 @@ struct ProdScalars {
 };
 
 struct FastSmem {
-    double2 A[2][TILE][NB_MAX];     // (u~_n[k], d w~[k]) for k = 8 b + e, indexed [e][b]
-    double2 C[2][TILE][NB_MAX];     // (u~_n[k], w~[k])
+    double2 A[2][TILE][NB_PAD];     // (u~_n[k], d w~[k]) for k = 8 b + e, indexed [e][b]
+    double2 C[2][TILE][NB_PAD];     // (u~_n[k], w~[k])
     double R[2][JP_MAX];            // renormalisation factors r[k] of the phase
     double P[2][NSLOT][JP_MAX];     // partial sums of g_n, natural column order
     double QF[2][MAT_WARPS];        // partial sums of u~ S~ u~^T per matrix warp
@@ -255,12 +258,12 @@ constexpr int P_PAR_BYTES = (int)sizeof(double) * NSLOT * JP_MAX;       // P[1] 
 template <int PAR, int I>
 __device__ __forceinline__ double2 mat_row_op(const MatConst &mc)
 {
-    return ((I < 4) ? mc.a_lo : mc.a_hi)[PAR * TILE * NB_MAX + (I & 3) * NB_MAX];
+    return ((I < 4) ? mc.a_lo : mc.a_hi)[PAR * TILE * NB_PAD + (I & 3) * NB_PAD];
 }
 template <int PAR, int J>
 __device__ __forceinline__ double2 mat_col_op(const MatConst &mc)
 {
-    return ((J < 4) ? mc.c_lo : mc.c_hi)[PAR * TILE * NB_MAX + (J & 3) * NB_MAX];
+    return ((J < 4) ? mc.c_lo : mc.c_hi)[PAR * TILE * NB_PAD + (J & 3) * NB_PAD];
 }
 
 template <int I>
