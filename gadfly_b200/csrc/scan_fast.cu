@@ -119,6 +119,7 @@ struct FastSmem {
     double Ht[HALF], Hde[HALF], Hrde[HALF];
     int Hcode[HALF];
     ProdScalars ps;
+    unsigned long long mb_ops[2];   // mbarriers "operands of matrix phase parity p ready" [chain -> matrix]
     int ctl[2];                     // per matrix phase parity: CTL_RENORM / CTL_STOP
     int stop;                       // first matrix phase that must not run
     int next;
@@ -131,6 +132,39 @@ __device__ __forceinline__ void bar_sync(int id, int count)
 __device__ __forceinline__ void bar_arrive(int id, int count)
 {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+// The hand-over chain -> matrix uses mbarriers instead of a named barrier: a named barrier would
+// also synchronise the eight matrix warps with each other at every phase (the fastest waits for the
+// slowest: measured 250 cycles per step), an mbarrier lets each matrix warp run at its own pace --
+// the two matrix warps of a scheduler drift apart, so that one warp's latency-bound prologue and
+// epilogue overlap the other's DFMA stream.
+#ifndef GF_OPS_MBAR
+#define GF_OPS_MBAR 1
+#endif
+__device__ __forceinline__ void mbar_init(const uint32_t addr, const int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_inval(const uint32_t addr)
+{
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(const uint32_t addr)
+{
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(const uint32_t addr, const uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "GF_MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra.uni GF_MBAR_DONE;\n"
+        "bra.uni GF_MBAR_WAIT;\n"
+        "GF_MBAR_DONE:\n"
+        "}\n" ::"r"(addr), "r"(parity) : "memory");
 }
 
 __device__ __forceinline__ double shfl_xor_d(double x, int m)
@@ -309,9 +343,14 @@ __device__ __forceinline__ void matrix_renorm(FastSmem &sm, double (&S)[TILE][TI
 // exchange inside the 2x2 group, the warp reduction of the quadratic form, stores and hand-over.
 template <int PAR>
 __device__ __forceinline__ int matrix_phase(FastSmem &sm, double (&S)[TILE][TILE], const MatConst &mc,
-                                            const int lane, const int warp)
+                                            const int lane, const int warp, const uint32_t use)
 {
+#if GF_OPS_MBAR
+    mbar_wait((uint32_t)__cvta_generic_to_shared(&sm.mb_ops[PAR]), use & 1u);
+#else
+    (void)use;
     bar_sync(BAR_OPS + PAR, N_OPS);
+#endif
     double uj[TILE], wj[TILE];
     {
         double2 c;
@@ -398,9 +437,10 @@ __device__ __forceinline__ void matrix_loop(FastSmem &sm, const int mt, const in
 
     // the chain stops the matrix warps only at a phase it has not released yet
     for (int n = 0;;) {
-        if (matrix_phase<0>(sm, S, mc, lane, warp) & CTL_STOP) break;
+        const uint32_t use = (uint32_t)n >> 1;   // this is the use-th phase of either parity
+        if (matrix_phase<0>(sm, S, mc, lane, warp, use) & CTL_STOP) break;
         if (++n >= N) break;
-        if (matrix_phase<1>(sm, S, mc, lane, warp) & CTL_STOP) break;
+        if (matrix_phase<1>(sm, S, mc, lane, warp, use) & CTL_STOP) break;
         if (++n >= N) break;
     }
 }
@@ -744,6 +784,18 @@ __device__ __forceinline__ void chain_reduce2_cta(FastSmem &sm, int hw, int lane
     b = (v0.y + v1.y) + v2.y;
 }
 
+// chain -> matrix: the operands of a matrix phase of parity par are in shared memory
+__device__ __forceinline__ void ops_arrive(FastSmem &sm, const int par, const int lane)
+{
+#if GF_OPS_MBAR
+    __syncwarp();
+    if (lane == 0) mbar_arrive((uint32_t)__cvta_generic_to_shared(&sm.mb_ops[par]));
+#else
+    (void)sm; (void)lane;
+    bar_arrive(BAR_OPS + par, N_OPS);
+#endif
+}
+
 // State the chain carries from step to step.  The serial path of the recurrence is kept as short
 // as possible: with t~_n = d_n w~_n = v~_n - h_n (no division) and tau_{n+1} = u~_{n+1} . t~_n,
 //   alpha_{n+1} = tau_{n+1} / d_n,   h_{n+1} = g_{n+1} + alpha_{n+1} t~_n,
@@ -803,6 +855,7 @@ __device__ __forceinline__ bool chain_step(FastSmem &sm, const ScanArgs &A, Chai
     const double2 u1 = sm.RU[s1][tix];
     const double2 u2 = sm.RU[s2][tix];
     const double r2 = sm.Rr[s2][tix];
+    const int ctl2 = sm.Rflag[s2] ? CTL_RENORM : 0;   // read here: off the critical section below
     double gpart = 0.0;
     if (n > 0) gpart = solver_update<MODE>(A, st, c, n - 1, gamma_prev, u0, r0);
 
@@ -847,8 +900,8 @@ __device__ __forceinline__ bool chain_step(FastSmem &sm, const ScanArgs &A, Chai
             sm.C[PAR][c.ke + 1][c.kb] = make_double2(u2.y, ws1);
             *reinterpret_cast<double2 *>(&sm.R[PAR][c.k0]) = make_double2(r2, r2);
         }
-        if (c.ht == 0) sm.ctl[PAR] = sm.Rflag[s2] ? CTL_RENORM : 0;
-        bar_arrive(BAR_OPS + PAR, N_OPS);
+        if (c.ht == 0) sm.ctl[PAR] = ctl2;
+        ops_arrive(sm, PAR, c.lane);
     }
     // ---- off the matrix' critical path --------------------------------------------------------
     double tau, gamma;
@@ -902,8 +955,8 @@ __device__ __forceinline__ void chain_loop(FastSmem &sm, const ScanArgs &A, cons
         sm.R[1][c.k0] = r1; sm.R[1][c.k0 + 1] = r1;
     }
     if (ht == 0) { sm.ctl[0] = 0; sm.ctl[1] = (N > 1 && sm.Rflag[1]) ? CTL_RENORM : 0; }
-    bar_arrive(BAR_OPS + 0, N_OPS);
-    if (N > 1) bar_arrive(BAR_OPS + 1, N_OPS);
+    ops_arrive(sm, 0, c.lane);
+    if (N > 1) ops_arrive(sm, 1, c.lane);
 
     ChainState st;
     st.tc = st.ts = st.wc = st.ws = st.Fc = st.Fs = st.alpha = st.tau = 0.0;
@@ -927,7 +980,7 @@ __device__ __forceinline__ void chain_loop(FastSmem &sm, const ScanArgs &A, cons
                 const int par = n & 1;
                 fail = n + 1;
                 if (ht == 0) { sm.stop = n + 2; sm.ctl[par] = CTL_STOP; }
-                if (n + 2 < N) bar_arrive(BAR_OPS + par, N_OPS);
+                if (n + 2 < N) ops_arrive(sm, par, c.lane);
                 if (n + 1 < N) bar_sync(BAR_PART + (par ^ 1), N_OPS);
                 drain = true;
             }
@@ -958,12 +1011,24 @@ __device__ __forceinline__ void chain_loop(FastSmem &sm, const ScanArgs &A, cons
 struct SeqInfo {
     int b, Jc, nsb;
     int N;
+    bool first = true;
 };
 
 __device__ __forceinline__ bool next_sequence(FastSmem &sm, const ScanArgs &A, const int tid, SeqInfo &q)
 {
     __syncthreads();   // everybody is done with the previous sequence
-    if (tid == 0) sm.next = atomicAdd(A.counter, 1);
+    if (tid == 0) {
+        sm.next = atomicAdd(A.counter, 1);
+#if GF_OPS_MBAR
+        // one arrival per chain warp; the phase parities restart with every sequence
+        for (int p = 0; p < 2; ++p) {
+            const uint32_t mb = (uint32_t)__cvta_generic_to_shared(&sm.mb_ops[p]);
+            if (!q.first) mbar_inval(mb);
+            mbar_init(mb, CH_THREADS / 32);
+        }
+#endif
+    }
+    q.first = false;
     // operand buffers (padding columns must read as zero) and partial sums
     {
         double *z = reinterpret_cast<double *>(&sm.A[0][0][0]);

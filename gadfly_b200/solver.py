@@ -46,7 +46,9 @@ class LinAlgError(Exception):
 
 
 def library_path():
-    return os.path.join(_HERE, _LIBNAME)
+    """In-tree library; ``$GADFLY_B200_LIB`` selects another build of the same C ABI (kernel A/B
+    experiments, tools/ab_scan.py)."""
+    return os.environ.get("GADFLY_B200_LIB") or os.path.join(_HERE, _LIBNAME)
 
 
 _lib = None

@@ -16,8 +16,13 @@ steps = float(sys.argv[2])
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
-h = rows[1]
-data = rows[2:]
+# one section per profiled kernel: "Kernel Name" row, header row, instruction rows
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"] + [len(rows)]
+kidx = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+sec = rows[starts[kidx]:starts[kidx + 1]]
+print("kernel:", sec[0][1][:80])
+h = sec[1]
+data = [r for r in sec[2:] if len(r) == len(h)]
 iS, iE, iSrc = h.index("# Samples"), h.index("Instructions Executed"), h.index("Source")
 stalls = [i for i, n in enumerate(h) if n.startswith("stall_") and "Not Issued" not in n]
 tot = sum(float(r[iS]) for r in data)
