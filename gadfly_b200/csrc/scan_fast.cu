@@ -36,6 +36,9 @@
 //      alpha_n^2).  Synchronisation is by named barriers (producer bar.arrive, consumer
 //      bar.sync) over double-buffered operands and partial sums.
 #include "common.cuh"
+#ifdef GF_TIMING
+#include <cstdio>   // debug builds (tools/build_variant.sh x -DGF_TIMING): per-role cycle counts via printf
+#endif
 
 namespace gf {
 
@@ -57,6 +60,11 @@ constexpr int NSLOT = NSB_MAX + 1;   // partial-sum slots per column
 // of a warp then hit complementary banks and the 16-byte stores run conflict-free.
 constexpr int CTL_RENORM = 1, CTL_STOP = 2;
 __host__ __device__ constexpr int pchunk(int chunk, int slot) { return chunk ^ ((slot + (chunk >> 3)) & 1); }
+#ifndef GF_QF_STAGES
+#define GF_QF_STAGES 5               // butterfly stages of the quadratic form done in the matrix warps
+                                     // (measured: 4 = same speed, 3 = 4 % slower -- the chain is co-critical)
+#endif
+constexpr int QF_PER_WARP = 32 >> GF_QF_STAGES;   // what is left per warp is summed by the chain
 constexpr int RR = 16;               // row ring depth (two halves)
 constexpr int HALF = 8;
 constexpr int REG_MAT = 208;
@@ -93,7 +101,7 @@ struct FastSmem {
     double2 C[2][TILE][NB_PAD];     // (u~_n[k], w~[k])
     double R[2][JP_MAX];            // renormalisation factors r[k] of the phase
     double P[2][NSLOT][JP_MAX];     // partial sums of g_n, natural column order
-    double QF[2][MAT_WARPS];        // partial sums of u~ S~ u~^T per matrix warp
+    double QF[2][MAT_WARPS * QF_PER_WARP];   // partial sums of u~ S~ u~^T, QF_PER_WARP per matrix warp
     double2 red2[2][4];             // (alpha, gamma) per chain warp
     // row ring, written by the producer warp
     double2 RU[RR][JC_MAX];         // (u~ cos column, u~ sin column) per term
@@ -154,6 +162,17 @@ __device__ __forceinline__ void mbar_arrive(const uint32_t addr)
 {
     asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
 }
+__device__ __forceinline__ bool mbar_test(const uint32_t addr, const uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(const uint32_t addr, const uint32_t parity)
 {
     asm volatile(
@@ -166,6 +185,13 @@ __device__ __forceinline__ void mbar_wait(const uint32_t addr, const uint32_t pa
         "GF_MBAR_DONE:\n"
         "}\n" ::"r"(addr), "r"(parity) : "memory");
 }
+
+#ifndef GF_EARLY_TEST
+#define GF_EARLY_TEST 1
+#endif
+#ifndef GF_CTL_ASM
+#define GF_CTL_ASM 1
+#endif
 
 __device__ __forceinline__ double shfl_xor_d(double x, int m)
 {
@@ -243,6 +269,7 @@ __device__ __forceinline__ TileMap make_tile_map(int mt, int nsb)
 struct MatConst {
     const double2 *a_lo, *a_hi, *c_lo, *c_hi;  // in A[0] / C[0]: operands of local rows / columns 0 and 4
     uint32_t pr0, pc0;                // shared-space addresses in P[0] of the first row / column chunk stored
+    uint32_t ctl0;                    // shared-space address of ctl[0]
     int geom;                         // bi | bj << 8 | mr << 16 | mc << 20 | kind << 24 (rare paths)
     double qw;
 };
@@ -269,6 +296,7 @@ __device__ __forceinline__ MatConst make_mat_const(const FastSmem &sm, const Til
     const int cr = 4 * tm.bi + mr / 2, cc = 4 * tm.bj + mc / 2;
     m.pr0 = (uint32_t)__cvta_generic_to_shared(P2 + tm.slot_row * (JP_MAX / 2) + pchunk(cr, tm.slot_row));
     m.pc0 = (uint32_t)__cvta_generic_to_shared(P2 + tm.slot_col * (JP_MAX / 2) + pchunk(cc, tm.slot_col));
+    m.ctl0 = (uint32_t)__cvta_generic_to_shared(&sm.ctl[0]);
     // weight of this tile in the quadratic form: off-diagonal tiles stand for their mirror too
     m.qw = (tm.kind == 3) ? 0.0 : ((tm.bi == tm.bj) ? 1.0 : 2.0);
     return m;
@@ -300,11 +328,27 @@ __device__ __forceinline__ double2 mat_col_op(const MatConst &mc)
     return ((J < 4) ? mc.c_lo : mc.c_hi)[PAR * TILE * NB_PAD + (J & 3) * NB_PAD];
 }
 
+#ifndef GF_RP_TAIL
+#define GF_RP_TAIL 1
+#endif
 template <int I>
 __device__ __forceinline__ void matrix_row_pair(const double2 a0, const double2 a1, double (&S)[TILE][TILE],
                                                 const double (&uj)[TILE], const double (&wj)[TILE],
                                                 double (&rowp)[TILE], double (&colp)[TILE])
 {
+#if GF_RP_TAIL
+    // update and column sums only: 16 independent updates, then 8 chains of depth 2
+    (void)uj; (void)rowp;
+    double T0[TILE], T1[TILE];
+#pragma unroll
+    for (int j = 0; j < TILE; ++j) T0[j] = fma(a0.y, wj[j], S[I][j]);
+#pragma unroll
+    for (int j = 0; j < TILE; ++j) T1[j] = fma(a1.y, wj[j], S[I + 1][j]);
+#pragma unroll
+    for (int j = 0; j < TILE; ++j) { S[I][j] = T0[j]; colp[j] = fma(a0.x, T0[j], colp[j]); }
+#pragma unroll
+    for (int j = 0; j < TILE; ++j) { S[I + 1][j] = T1[j]; colp[j] = fma(a1.x, T1[j], colp[j]); }
+#else
     double rp0 = 0.0, rp1 = 0.0;
 #pragma unroll
     for (int j = 0; j < TILE; ++j) {
@@ -317,6 +361,29 @@ __device__ __forceinline__ void matrix_row_pair(const double2 a0, const double2 
         rp1 = fma(T1, uj[j], rp1);
     }
     rowp[I] = rp0; rowp[I + 1] = rp1;
+#endif
+}
+
+// Row sums of the updated tile, after the update: 16 independent chains of depth 4 (every row in
+// two halves), so that one warp alone keeps the FP64 pipe busy (a dependent DFMA can issue 23
+// cycles after its producer: at 2 cycles per DFMA that takes >= 12 independent instructions).
+__device__ __forceinline__ void matrix_row_sums(const double (&S)[TILE][TILE], const double (&uj)[TILE],
+                                                double (&rowp)[TILE])
+{
+    double ra[TILE], rb[TILE];
+#pragma unroll
+    for (int i = 0; i < TILE; ++i) ra[i] = S[i][0] * uj[0];
+#pragma unroll
+    for (int i = 0; i < TILE; ++i) rb[i] = S[i][1] * uj[1];
+#pragma unroll
+    for (int j = 2; j < TILE; j += 2) {
+#pragma unroll
+        for (int i = 0; i < TILE; ++i) ra[i] = fma(S[i][j], uj[j], ra[i]);
+#pragma unroll
+        for (int i = 0; i < TILE; ++i) rb[i] = fma(S[i][j + 1], uj[j + 1], rb[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < TILE; ++i) rowp[i] = ra[i] + rb[i];
 }
 
 // frame change: S~ <- r r^T o (S~ + d w~ w~^T); the rank-1 term is consumed here (rare)
@@ -339,17 +406,41 @@ __device__ __forceinline__ void matrix_renorm(FastSmem &sm, double (&S)[TILE][TI
     for (int e = 0; e < TILE; ++e) wj[e] = 0.0;
 }
 
+#ifdef GF_TIMING
+#define g_wait tm_wait
+#define g_notready tm_notready
+#endif
 // One phase of a matrix thread: wait for the operands, (renormalisation,) the arithmetic, the
 // exchange inside the 2x2 group, the warp reduction of the quadratic form, stores and hand-over.
 template <int PAR>
 __device__ __forceinline__ int matrix_phase(FastSmem &sm, double (&S)[TILE][TILE], const MatConst &mc,
-                                            const int lane, const int warp, const uint32_t use)
+                                            const int lane, const int warp, const uint32_t use,
+                                            const bool last, bool &ready
+#ifdef GF_TIMING
+                                            , long long &tm_wait, int &tm_notready
+#endif
+                                            )
 {
+#ifdef GF_TIMING
+    const long long tw0 = clock64();
+#endif
 #if GF_OPS_MBAR
-    mbar_wait((uint32_t)__cvta_generic_to_shared(&sm.mb_ops[PAR]), use & 1u);
+    // `ready`: the test issued in the previous phase (its latency hidden there) already saw the
+    // operands of this phase
+    if (!ready) mbar_wait((uint32_t)__cvta_generic_to_shared(&sm.mb_ops[PAR]), use & 1u);
 #else
     (void)use;
     bar_sync(BAR_OPS + PAR, N_OPS);
+#endif
+#ifdef GF_TIMING
+    g_wait += clock64() - tw0;
+    g_notready += ready ? 0 : 1;
+#endif
+    // control word: loaded through a per-thread address so that the test is an ordinary predicate
+    // (the uniform-datapath form costs an R2UR round trip in front of the DFMA stream)
+#if GF_CTL_ASM
+    int ctl;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ctl) : "r"(mc.ctl0 + PAR * 4u) : "memory");
 #endif
     double uj[TILE], wj[TILE];
     {
@@ -363,7 +454,9 @@ __device__ __forceinline__ int matrix_phase(FastSmem &sm, double (&S)[TILE][TILE
         c = mat_col_op<PAR, 6>(mc); uj[6] = c.x; wj[6] = c.y;
         c = mat_col_op<PAR, 7>(mc); uj[7] = c.x; wj[7] = c.y;
     }
+#if !GF_CTL_ASM
     const int ctl = sm.ctl[PAR];
+#endif
     if (ctl) {
         if (ctl & CTL_STOP) return ctl;
         matrix_renorm<PAR>(sm, S, mc.geom, wj);
@@ -378,6 +471,9 @@ __device__ __forceinline__ int matrix_phase(FastSmem &sm, double (&S)[TILE][TILE
     matrix_row_pair<2>(mat_row_op<PAR, 2>(mc), mat_row_op<PAR, 3>(mc), S, uj, wj, rowp, colp);
     matrix_row_pair<4>(mat_row_op<PAR, 4>(mc), mat_row_op<PAR, 5>(mc), S, uj, wj, rowp, colp);
     matrix_row_pair<6>(mat_row_op<PAR, 6>(mc), mat_row_op<PAR, 7>(mc), S, uj, wj, rowp, colp);
+#if GF_RP_TAIL
+    matrix_row_sums(S, uj, rowp);
+#endif
 
     // quadratic form u~ S~ u~^T: this tile's share, reduced over the warp
     double qf0 = colp[0] * uj[0], qf1 = colp[1] * uj[1];
@@ -385,6 +481,12 @@ __device__ __forceinline__ int matrix_phase(FastSmem &sm, double (&S)[TILE][TILE
     for (int j = 2; j < TILE; j += 2) { qf0 = fma(colp[j], uj[j], qf0); qf1 = fma(colp[j + 1], uj[j + 1], qf1); }
     double qf = (qf0 + qf1) * mc.qw;
 
+#if GF_OPS_MBAR && GF_EARLY_TEST
+    // are the operands of the next phase there already?  (normally yes: asked here, used at the top
+    // of the next phase)
+    ready = last ? false
+                 : mbar_test((uint32_t)__cvta_generic_to_shared(&sm.mb_ops[PAR ^ 1]), (use + PAR) & 1u);
+#endif
     // 2x2 group: combine the two tiles of a block row (lane ^ 1) and of a block column (lane ^ 2)
     // (each lane keeps four of the eight sums: rows 4 cj.., columns 4 ri..)
     const bool hr = geom_mr(mc.geom) != 0, hc = geom_mc(mc.geom) != 0;
@@ -399,8 +501,8 @@ __device__ __forceinline__ int matrix_phase(FastSmem &sm, double (&S)[TILE][TILE
         cs[q] = keep_c + shfl_xor_d(send_c, 2);
     }
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) qf += shfl_xor_d(qf, off);
-    if (lane == 0) sm.QF[PAR][warp] = qf;
+    for (int off = 16; off >= QF_PER_WARP; off >>= 1) qf += shfl_xor_d(qf, off);
+    if (lane < QF_PER_WARP) sm.QF[PAR][warp * QF_PER_WARP + lane] = qf;
 
     const int kind = geom_kind(mc.geom);
     if (kind == 0) {
@@ -436,13 +538,29 @@ __device__ __forceinline__ void matrix_loop(FastSmem &sm, const int mt, const in
         for (int j = 0; j < TILE; ++j) S[i][j] = 0.0;
 
     // the chain stops the matrix warps only at a phase it has not released yet
+    bool ready = false;
+#ifdef GF_TIMING
+    long long tm_wait = 0; int tm_notready = 0;
+    const long long tm_start = clock64();
+#define GF_TM_ARGS , tm_wait, tm_notready
+#else
+#define GF_TM_ARGS
+#endif
     for (int n = 0;;) {
         const uint32_t use = (uint32_t)n >> 1;   // this is the use-th phase of either parity
-        if (matrix_phase<0>(sm, S, mc, lane, warp, use) & CTL_STOP) break;
-        if (++n >= N) break;
-        if (matrix_phase<1>(sm, S, mc, lane, warp, use) & CTL_STOP) break;
+        int ctl = matrix_phase<0>(sm, S, mc, lane, warp, use, n + 1 >= N, ready GF_TM_ARGS);
+        if (!(ctl & CTL_STOP)) {
+            if (++n >= N) break;
+            ctl = matrix_phase<1>(sm, S, mc, lane, warp, use, n + 1 >= N, ready GF_TM_ARGS);
+        }
+        if (ctl & CTL_STOP) break;
         if (++n >= N) break;
     }
+#ifdef GF_TIMING
+    if (blockIdx.x == 0 && lane == 0)
+        printf("matrix warp %d: %.1f cyc/phase, ops wait %.1f cyc/phase, not ready at early test %.3f\n", warp,
+               (double)(clock64() - tm_start) / N, (double)tm_wait / N, (double)tm_notready / N);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------
@@ -810,6 +928,9 @@ struct ChainState {
     double rd;              // 1 / d_{n-1}
     double zp;              // y_{n-1} (log-likelihood) or sqrt(d_{n-1}) n_{n-1} (sampling)
     double logdet, prod, quad;
+#ifdef GF_TIMING
+    long long t_part = 0, t_crit = 0;
+#endif
 };
 
 struct ChainConst {
@@ -859,7 +980,14 @@ __device__ __forceinline__ bool chain_step(FastSmem &sm, const ScanArgs &A, Chai
     double gpart = 0.0;
     if (n > 0) gpart = solver_update<MODE>(A, st, c, n - 1, gamma_prev, u0, r0);
 
+#ifdef GF_TIMING
+    const long long tp0 = clock64();
+#endif
     bar_sync(BAR_PART + PAR, N_OPS);
+#ifdef GF_TIMING
+    st.t_part += clock64() - tp0;
+    const long long tc0 = clock64();
+#endif
     // g_n: unused slots hold zeros, so the sum always runs over all of them (two batches of six
     // slots to keep the register footprint of the loads small)
     static_assert(NSLOT == 12, "summation tree below is written for 12 slots");
@@ -884,9 +1012,19 @@ __device__ __forceinline__ bool chain_step(FastSmem &sm, const ScanArgs &A, Chai
     const double red = chain_reduce2_warp(c.lane, tpart, gpart);
 
     // pivot, beside the reduction: d_n = a_n - (u~ S~(n-1) u~^T + alpha_n tau_n)
-    const double2 *Q2 = reinterpret_cast<const double2 *>(&sm.QF[PAR][0]);
-    const double2 q0 = Q2[0], q1 = Q2[1], q2 = Q2[2], q3 = Q2[3];
-    const double qf = ((q0.x + q0.y) + (q1.x + q1.y)) + ((q2.x + q2.y) + (q3.x + q3.y));
+    double qf;
+    {
+        const double2 *Q2 = reinterpret_cast<const double2 *>(&sm.QF[PAR][0]);
+        constexpr int NQ = MAT_WARPS * QF_PER_WARP / 2;
+        double2 q[NQ];
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) q[i] = Q2[i];
+#pragma unroll
+        for (int w = NQ / 2; w >= 1; w >>= 1)
+#pragma unroll
+            for (int i = 0; i < w; ++i) { q[i].x += q[i + w].x; q[i].y += q[i + w].y; }
+        qf = q[0].x + q[0].y;
+    }
     const double dn = ra - fma(st.alpha, st.tau, qf);
     if (!(dn > 0.0)) return false;
     const double rd = fast_rcp(dn);
@@ -903,6 +1041,9 @@ __device__ __forceinline__ bool chain_step(FastSmem &sm, const ScanArgs &A, Chai
         if (c.ht == 0) sm.ctl[PAR] = ctl2;
         ops_arrive(sm, PAR, c.lane);
     }
+#ifdef GF_TIMING
+    st.t_crit += clock64() - tc0;
+#endif
     // ---- off the matrix' critical path --------------------------------------------------------
     double tau, gamma;
     chain_reduce2_cta<PAR>(sm, c.hw, c.lane, red, tau, gamma);
@@ -998,6 +1139,11 @@ __device__ __forceinline__ void chain_loop(FastSmem &sm, const ScanArgs &A, cons
             A.out_x[c.n0 + N - 1] = st.zp + gamma_prev;
         }
     }
+#ifdef GF_TIMING
+    if (blockIdx.x == 0 && c.lane == 0)
+        printf("chain warp %d: PART wait %.1f cyc/step, critical section %.1f cyc/step\n", c.hw,
+               (double)st.t_part / N, (double)st.t_crit / N);
+#endif
     if (ht == 0) {
         if (st.prod != 1.0) st.logdet += log(st.prod);
         A.logdet[b] = st.logdet;

@@ -175,6 +175,12 @@ int main()
     RUN("DFMA 2 warps/SMSP ILP4", "4 DFMA each", k_dfma<4><<<1, 512>>>(out, cyc, 2));
     RUN("DFMA 2 warps/SMSP ILP8", "8 DFMA each", k_dfma<8><<<1, 512>>>(out, cyc, 2));
     RUN("DFMA 3 warps/SMSP ILP8", "8 DFMA each", k_dfma<8><<<1, 512>>>(out, cyc, 3));
+    RUN("DFMA 1 warp ILP16", "16 DFMA", k_dfma<16><<<1, 512>>>(out, cyc, 1));
+    RUN("DFMA 1 warp ILP32", "32 DFMA", k_dfma<32><<<1, 512>>>(out, cyc, 1));
+    RUN("DFMA 2 warps/SMSP ILP16", "16 DFMA each", k_dfma<16><<<1, 512>>>(out, cyc, 2));
+    RUN("DFMA 2 warps/SMSP ILP32", "32 DFMA each", k_dfma<32><<<1, 512>>>(out, cyc, 2));
+    RUN("DFMA 3 warps/SMSP ILP16", "16 DFMA each", k_dfma<16><<<1, 512>>>(out, cyc, 3));
+    RUN("DFMA 4 warps/SMSP ILP16", "16 DFMA each", k_dfma<16><<<1, 512>>>(out, cyc, 4));
     RUN("DADD dependent, idle SMSP", "DADD", k_contend<<<1, 512>>>(out, cyc, 0));
     RUN("DADD dependent vs 1 saturating warp", "DADD", k_contend<<<1, 512>>>(out, cyc, 1));
     RUN("DADD dependent vs 2 saturating warps", "DADD", k_contend<<<1, 512>>>(out, cyc, 2));
