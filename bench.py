@@ -287,6 +287,20 @@ def run_b200(args):
         except Exception:
             pass
         hbm_achieved = 24.0 * B * N / (dom_ms * 1e-3) / 1e9
+        # DRAM traffic of one launch: bytes per point from the committed ncu capture of the same
+        # kernel (profiles/r1_v5_traffic.json) x the points of this launch
+        traffic, traffic_src = None, None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r1_v5_traffic.json")) as fh:
+                tj = json.load(fh)
+            for name in (f"scan ({dom})", "scan (loglike)"):
+                if name in tj:
+                    per_point = (tj[name]["dram_bytes_read"] + tj[name]["dram_bytes_write"]) / tj["points_per_launch"]
+                    traffic = per_point * B * N
+                    traffic_src = f"{name}: {per_point:.2f} B/point measured by ncu (profiles/r1_v5_traffic.json)"
+                    break
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -310,7 +324,7 @@ def run_b200(args):
                 "kernel_ms": {"loglike": ll_ms, "sample": sm_ms},
                 "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
                         "frac": hbm_achieved / hbm_peak, "bytes_per_step": 24},
-                "traffic": None,
+                "traffic": traffic, "traffic_source": traffic_src,
             },
             "gpu_launches": int(launches),
             "clocks": clk,

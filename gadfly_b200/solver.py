@@ -376,7 +376,10 @@ class Solver:
     # -- K5 ----------------------------------------------------------------------------
     def psd(self, kb, omega, out=None, n_omega=None, flags=0):
         """-> psd[B, F] of the (exposure-integrated) kernels at angular frequencies omega."""
-        F = int(n_omega) if n_omega is not None else int(np.size(omega))
+        if n_omega is not None:
+            F = int(n_omega)
+        else:   # ndarray or device tensor
+            F = int(omega.numel()) if hasattr(omega, "numel") else int(np.size(omega))
         pw, keep = _addr(omega, count=F, name="omega")
         out, po = _out(out, (kb.B, F))
         j_off, pj = _i64(kb.j_off)
