@@ -8,3 +8,4 @@ from .gp import *  # noqa: F401,F403
 from .psd import *  # noqa: F401,F403
 from .solver import Solver, KernelBatch, LinAlgError, SolverUnavailable  # noqa: F401
 from . import batch  # noqa: F401
+from . import feeder  # noqa: F401,E402

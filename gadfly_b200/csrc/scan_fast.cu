@@ -67,8 +67,14 @@ __host__ __device__ constexpr int pchunk(int chunk, int slot) { return chunk ^ (
 constexpr int QF_PER_WARP = 32 >> GF_QF_STAGES;   // what is left per warp is summed by the chain
 constexpr int RR = 16;               // row ring depth (two halves)
 constexpr int HALF = 8;
-constexpr int REG_MAT = 208;
-constexpr int REG_HLP = 88;
+#ifndef GF_REG_MAT
+#define GF_REG_MAT 208
+#endif
+#ifndef GF_REG_HLP
+#define GF_REG_HLP 88
+#endif
+constexpr int REG_MAT = GF_REG_MAT;
+constexpr int REG_HLP = GF_REG_HLP;
 constexpr int REG_LAUNCH = 168;      // registers per thread at launch (65536 / 384, multiple of 8)
 // setmaxnreg.inc only draws on what the CTA's own warps released: the matrix warps would wait
 // forever if the helpers did not give back enough

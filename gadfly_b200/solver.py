@@ -180,6 +180,14 @@ class KernelBatch:
         if self.B and int(np.max(np.diff(self.j_off))) * 2 > GF_MAX_J:
             raise ValueError(f"kernel state wider than GF_MAX_J = {GF_MAX_J}")
 
+    @staticmethod
+    def for_stars(mass, radius, temperature, luminosity, texp_s=60.0, bandpass='SOHO VIRGO', alpha=None):
+        """Batched ``Hyperparameters.for_star`` + kernel assembly for arrays of stars
+        (gadfly_b200/feeder.py): ~100x faster than one kernel object per star."""
+        from .feeder import kernel_batch_for_stars
+        return kernel_batch_for_stars(mass, radius, temperature, luminosity, texp_s=texp_s,
+                                      bandpass=bandpass, alpha=alpha)
+
     @property
     def J(self):
         return 2 * np.diff(self.j_off)

@@ -241,6 +241,50 @@ def test_device_pointers_and_async(solver, solar_kernel):
     assert solver.last_kernel_ms > 0 and solver.launch_count > 0
 
 
+def test_psd_device_tensors(solver, solar_kernel, giant_kernel):
+    """Frequency grid and output resident in HBM: same numbers as the host-array call."""
+    import torch
+    dev = torch.device('cuda', solver.device)
+    kb = KernelBatch([solar_kernel, giant_kernel])
+    omega = 2 * np.pi * np.linspace(0.5, 6000.0, 5000)
+    ref = solver.psd(kb, omega)
+    od = torch.from_numpy(omega).to(dev)
+    out = torch.empty(2 * len(omega), dtype=torch.float64, device=dev)
+    solver.psd(kb, od, out=out)
+    np.testing.assert_array_equal(out.cpu().numpy().reshape(2, -1), ref)
+
+
+def test_batched_feeder_end_to_end(solver):
+    """Stars -> KernelBatch.for_stars (batched feeder) -> fused log-likelihood, against the
+    per-star kernel objects through the same kernel and against the CPU oracle."""
+    import warnings
+    stars = [(1.0, 1.0, 5777.0, 1.0), (1.1, 1.6, 6100.0, 3.2), (0.9, 1.4, 5500.0, 2.2), (1.3, 2.5, 5900.0, 6.0)]
+    M, R, Tt, L = (np.array(x) for x in zip(*stars))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        kernels = [g.StellarOscillatorKernel(
+            g.Hyperparameters.for_star(m, r, t, l, bandpass='SOHO VIRGO', quiet=True), texp=1 * g.units.min)
+            for m, r, t, l in stars]
+    kb_ref, kb = KernelBatch(kernels), KernelBatch.for_stars(M, R, Tt, L)
+    for b in (kb_ref, kb):
+        b.ddiag = b.ddiag + 30.0 ** 2          # yerr = 30 ppm
+    N = 1500
+    t = np.arange(N) * 6e-5
+    y = np.random.default_rng(11).standard_normal((len(stars), N)) * 200
+    geom = Geometry.shared_t(len(stars), N)
+    ld0, q0, s0 = solver.loglike(kb_ref, geom, t, y)
+    ld1, q1, s1 = solver.loglike(kb, geom, t, y)
+    assert s0.tolist() == [0] * 4 and s1.tolist() == [0] * 4
+    np.testing.assert_allclose(ld1, ld0, rtol=1e-9)
+    np.testing.assert_allclose(q1, q0, rtol=1e-8)
+    for b, k in enumerate(kernels):
+        sc = list(k.scan_coefficients())
+        sc[-1] += 30.0 ** 2
+        logdet, quad, status = oracle.stream(0, tuple(sc), t, y[b])
+        assert status == 0
+        assert ld0[b] == pytest.approx(logdet, rel=RTOL) and q0[b] == pytest.approx(quad, rel=RTOL)
+
+
 def test_round_trip_sample_psd_statistics(solver, solar_kernel):
     """The reference's only hot-path test (gadfly/tests/test_core.py:17-49): samples drawn from
     the kernel have the kernel's power spectrum (binned FFT PSD within 5 sigma, 3-1000 uHz)."""

@@ -202,3 +202,39 @@ def test_power_spectrum_fft_normalisation():
     b = ps.bin(10)
     assert len(b.frequency) == 10 and b.error is not None
     assert len(ps.cutout(100 * u.uHz, 1000 * u.uHz).frequency) < len(ps.frequency)
+
+
+def test_batched_feeder_matches_per_star():
+    """gadfly_b200/feeder.py against Hyperparameters.for_star + StellarOscillatorKernel
+    + KernelBatch star by star: same terms kept, coefficients to a few ulp (the diagonal correction
+    is a cancelling sum: compared on the scale of k(0))."""
+    import warnings
+    from gadfly_b200 import feeder
+    stars = [(1.0, 1.0, 5777.0, 1.0), (0.9, 10.0, 4919.0, 52.3), (1.32, 11.26, 4923.0, 66.8),
+             (1.1, 1.6, 6100.0, 3.2), (2.0, 20.7, 4364.0, 146.0), (0.9, 1.4, 5500.0, 2.2)]
+    M, R, T, L = (np.array(x) for x in zip(*stars))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        kernels = [g.StellarOscillatorKernel(
+            g.Hyperparameters.for_star(m, r, t, l, bandpass='SOHO VIRGO', quiet=True), texp=1 * u.min)
+            for m, r, t, l in stars]
+    from gadfly_b200.solver import KernelBatch
+    ref = KernelBatch(kernels)
+    hpb = feeder.for_stars(M, R, T, L)
+    got = feeder.kernel_batch_from_sho(hpb, kernels[0].delta)
+    assert np.array_equal(got.j_off, ref.j_off)
+    assert got.j_off[1] == 86 and got.j_off[2] - got.j_off[1] == 62      # Sun, KIC 9333184
+    np.testing.assert_allclose(got.base, ref.base, rtol=1e-11)
+    np.testing.assert_allclose(got.coef, ref.coef, rtol=1e-11)
+    k0 = np.array([ref.coef[ref.j_off[b]:ref.j_off[b + 1], 0].sum() for b in range(ref.B)])
+    assert np.all(np.abs(got.ddiag - ref.ddiag) <= 1e-9 * k0)
+    assert np.array_equal(got.delta, ref.delta)
+    # the reference's list-of-dicts view of one star
+    sun = hpb.star(0)
+    assert len(sun) == 86 and sun[0]['hyperparameters']['Q'] == pytest.approx(0.6)
+    # one-call form, and the alpha override
+    kb = KernelBatch.for_stars(M, R, T, L, texp_s=60.0)
+    np.testing.assert_allclose(kb.coef, ref.coef, rtol=1e-11)
+    kb2 = KernelBatch.for_stars(M, R, T, L, alpha=2.0)
+    gran = slice(0, 5)
+    np.testing.assert_allclose(kb2.base[gran, 0], 2.0 * kb.base[gran, 0], rtol=1e-13)

@@ -32,64 +32,41 @@ def star_table():
     return np.genfromtxt(path, delimiter=",", names=True, skip_header=1)
 
 
-def kepler_like_kernels(n, seed):
-    """cfg2 / cfg5 population: rows drawn with replacement, jittered by their sig_* columns."""
-    import warnings
-    import gadfly_b200 as g
+def kepler_like_batch(n, seed):
+    """cfg2 / cfg5 population: rows drawn with replacement, jittered by their sig_* columns; built
+    by the batched feeder (gadfly_b200/feeder.py).  Returns (KernelBatch, feeder seconds)."""
+    from gadfly_b200 import feeder
     tab = star_table()
     rng = np.random.default_rng(seed)
     rows = rng.integers(0, len(tab), n)
-    kernels = []
-    for k, i in enumerate(rows):
-        r = tab[i]
-        M = max(r["mass"] + rng.standard_normal() * r["sig_mass"], 0.3)
-        R = max(r["rad"] + rng.standard_normal() * r["sig_rad"], 0.3)
-        T = max(r["teff"] + rng.standard_normal() * r["sig_teff"], 3500.0)
-        L = max(r["lum"] + rng.standard_normal() * r["sig_lum"], 0.05)
-        with warnings.catch_warnings():
-            warnings.simplefilter("ignore")
-            hp = g.Hyperparameters.for_star(M, R, T, L, bandpass='SOHO VIRGO', quiet=True)
-            kernels.append(g.StellarOscillatorKernel(hp, texp=1 * g.units.min))
-    return kernels
+    z = rng.standard_normal((n, 4))
+    r = tab[rows]
+    M = np.maximum(r["mass"] + z[:, 0] * r["sig_mass"], 0.3)
+    R = np.maximum(r["rad"] + z[:, 1] * r["sig_rad"], 0.3)
+    T = np.maximum(r["teff"] + z[:, 2] * r["sig_teff"], 3500.0)
+    L = np.maximum(r["lum"] + z[:, 3] * r["sig_lum"], 0.05)
+    t0 = time.perf_counter()
+    kb = feeder.kernel_batch_for_stars(M, R, T, L, texp_s=60.0, bandpass='SOHO VIRGO')
+    return kb, time.perf_counter() - t0
 
 
-def lattice_kernels(n, seed):
-    """cfg4 grid: solar hyper-parameters with S0, w0, Q of every term scaled by lattice factors."""
+def lattice_batch(n, seed):
+    """cfg4 grid: solar hyper-parameters with S0, w0, Q of every term scaled by lattice factors
+    0.9 .. 1.1 (a random subset of n points of the side^3 lattice)."""
     import gadfly_b200 as g
-    from gadfly_b200.terms import SHOTerm
+    from gadfly_b200 import feeder
     hp = g.Hyperparameters.for_sun()
+    S0, w0, Q = (np.array([q['hyperparameters'][k] for q in hp]) for k in ('S0', 'w0', 'Q'))
     side = int(np.ceil(n ** (1.0 / 3.0)))
     f = np.linspace(0.9, 1.1, side)
-    rng = np.random.default_rng(seed)
-    pts = rng.permutation(side ** 3)[:n]
-    kernels = []
-    for p in pts:
-        i, j, k = p // (side * side), (p // side) % side, p % side
-        terms = [SHOTerm(S0=q['hyperparameters']['S0'] * f[i], w0=q['hyperparameters']['w0'] * f[j],
-                         Q=q['hyperparameters']['Q'] * f[k]) for q in hp]
-        kernels.append(g.StellarOscillatorKernel(terms=terms, texp=1 * g.units.min))
-    return kernels
-
-
-def cached_batch(tag, n, seed, make):
-    """KernelBatch of the population `tag`, cached as plain arrays under variants/ (the host feeder
-    runs O(20 ms) per star; precomputing here keeps it out of the GPU box's clock)."""
-    from gadfly_b200.solver import KernelBatch
-    path = os.path.join(ROOT, "variants", f"{tag}_{n}_{seed}.npz")
-    if os.path.exists(path):
-        d = np.load(path)
-        kb = object.__new__(KernelBatch)
-        kb.B = int(d["B"]); kb.coef = d["coef"]; kb.base = d["base"]; kb.j_off = d["j_off"]
-        kb.ddiag = d["ddiag"]; kb.delta = d["delta"]
-        return kb, None, float(d["host_s"])
+    pts = np.random.default_rng(seed).permutation(side ** 3)[:n]
+    i, j, k = pts // (side * side), (pts // side) % side, pts % side
     t0 = time.perf_counter()
-    kernels = make(n, seed)
-    kb = KernelBatch(kernels)
-    host_s = time.perf_counter() - t0
-    os.makedirs(os.path.dirname(path), exist_ok=True)
-    np.savez(path, B=kb.B, coef=kb.coef, base=kb.base, j_off=kb.j_off, ddiag=kb.ddiag, delta=kb.delta,
-             host_s=host_s)
-    return kb, kernels, host_s
+    hpb = feeder.HyperparameterBatch((S0[None, :] * f[i][:, None]).ravel(), (w0[None, :] * f[j][:, None]).ravel(),
+                                     (Q[None, :] * f[k][:, None]).ravel(),
+                                     np.arange(n + 1, dtype=np.int64) * len(S0))
+    kb = feeder.kernel_batch_from_sho(hpb, 6e-5)
+    return kb, time.perf_counter() - t0
 
 
 def main():
@@ -98,15 +75,7 @@ def main():
     ap.add_argument("--grid", type=int, default=4096)
     ap.add_argument("--psd-stars", type=int, default=256)
     ap.add_argument("--json", default=None)
-    ap.add_argument("--prepare", action="store_true", help="only build and cache the kernel batches (no GPU)")
     args = ap.parse_args()
-    if args.prepare:
-        for tag, n, seed, make in (("kepler", args.stars, 1, kepler_like_kernels),
-                                   ("lattice", args.grid, 3, lattice_kernels),
-                                   ("kepler", args.psd_stars, 4, kepler_like_kernels)):
-            kb, _, host_s = cached_batch(tag, n, seed, make)
-            print(tag, n, "kernels", kb.B, "host feeder %.1f s" % host_s)
-        return
 
     import torch
     from gadfly_b200 import solver as S
@@ -118,7 +87,7 @@ def main():
     out = {"fp64_peak_tflops": peak / 1e12, "sm_count": info["sm_count"]}
 
     # ---- cfg2 -------------------------------------------------------------------------------
-    kb, _, host_s = cached_batch("kepler", args.stars, 1, kepler_like_kernels)
+    kb, host_s = kepler_like_batch(args.stars, 1)
     # white measurement noise yerr = 50 ppm as a scalar diagonal (added to the per-star ddiag):
     # without it ~7 % of these stars (slow red giants at 1-min cadence, k(0) ~ 1e7 ppm^2) are
     # numerically not positive definite -- the CPU oracle reports the same pivots <= 0, and
@@ -140,10 +109,10 @@ def main():
     for _ in range(2):
         solver.loglike(kb, geom, t, y, logdet=logdet, quad=quad, status=status)
     ms = solver.last_kernel_ms
-    # stars reported as not positive definite (status = 1 + index of the first pivot <= 0): the one
-    # the CPU oracle flags too (star 1455: a 2 % amplitude giant, k(0) = 3.8e8 ppm^2, all power
-    # below 32 uHz -- singular to FP64 at this cadence and noise level); they stop early, so the
-    # work is counted without them
+    # stars reported as not positive definite (status = 1 + index of the first pivot <= 0): the
+    # CPU oracle flags the same kind (2 % amplitude giants, k(0) > 1e8 ppm^2, all power below 32 uHz
+    # -- singular to FP64 at this cadence and noise level); they stop early, so the work is counted
+    # without them
     bad = status.cpu().numpy() != 0
     assert bad.sum() <= 4, bad.sum()
     ok_t = torch.as_tensor(~bad, device=dev)
@@ -158,7 +127,7 @@ def main():
     del y
 
     # ---- cfg4 -------------------------------------------------------------------------------
-    kb, _, host_s = cached_batch("lattice", args.grid, 3, lattice_kernels)
+    kb, host_s = lattice_batch(args.grid, 3)
     B, N = kb.B, 100000
     J = kb.J.astype(np.float64)
     # one light curve for every grid point: t is shared through t_off; the C ABI addresses y through
@@ -188,7 +157,7 @@ def main():
         del y
 
     # ---- cfg5 -------------------------------------------------------------------------------
-    kb, _, _ = cached_batch("kepler", args.psd_stars, 4, kepler_like_kernels)
+    kb, _ = kepler_like_batch(args.psd_stars, 4)
     F = 1000000
     omega = 2 * np.pi * np.linspace(0.01, 8333.0, F)
     omega_d = torch.as_tensor(omega, device=dev)
