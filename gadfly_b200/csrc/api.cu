@@ -26,13 +26,16 @@ cudaError_t launch_sweep(int op, int64_t B, const int64_t *n_off, const int64_t 
 cudaError_t launch_psd(int64_t B, const int64_t *j_off, const double *coef, const double *delta,
                        const double *omega, int64_t F, double *out, cudaStream_t stream);
 cudaError_t measure_fp64_peak(int sm_count, cudaStream_t stream, double *flops);
+cudaError_t launch_cond_mean(int64_t N, const double *t, int64_t M, const double *ts, int Jc,
+                             const double *coef, const double *alpha, double *scratch, double *mu,
+                             cudaStream_t stream);
 }  // namespace gf
 
 namespace {
 
 enum Slot {
     S_NOFF, S_TOFF, S_JOFF, S_WOFF, S_ORDER, S_COUNTER, S_T, S_Y, S_DIAG, S_COEF, S_DDIAG,
-    S_OUT, S_OUTW, S_LOGDET, S_QUAD, S_STATUS, S_OMEGA, S_DELTA, S_W, N_SLOTS
+    S_OUT, S_OUTW, S_LOGDET, S_QUAD, S_STATUS, S_OMEGA, S_DELTA, S_W, S_SCRATCH, N_SLOTS
 };
 
 struct Buf {
@@ -449,6 +452,36 @@ int gf_psd_batched(gf_handle h, int64_t B, const int64_t *j_off, const double *c
         Timer timer(h);
         GF_CUDA(h, gf::launch_psd(B, d_joff, d_coef, d_delta, d_omega, F, o.dev, h->stream));
         h->launches += (B + 65534) / 65535;
+    }
+    GF_CUDA(h, finish_out(h, o));
+    if (!(flags & GF_FLAG_ASYNC)) GF_CUDA(h, cudaStreamSynchronize(h->stream));
+    return GF_OK;
+}
+
+int gf_conditional_mean(gf_handle h, int64_t N, const double *t, int64_t M, const double *ts,
+                        int64_t Jc, const double *coef, const double *alpha, double *mu,
+                        uint32_t flags)
+{
+    if (!h) return GF_E_ARG;
+    if (N < 0 || M < 0 || Jc < 0) return fail(h, GF_E_ARG, "negative size");
+    if (M == 0) return GF_OK;
+    if (!ts || !mu || (N > 0 && (!t || !alpha)) || (Jc > 0 && !coef))
+        return fail(h, GF_E_ARG, "null data pointer");
+    if (Jc > 0x3fffffff) return fail(h, GF_E_ARG, "too many terms");
+    Guard guard(h->device);
+    const double *d_t, *d_ts, *d_coef, *d_alpha;
+    GF_CUDA(h, stage_in(h, S_T, t, (size_t)N, &d_t));
+    GF_CUDA(h, stage_in(h, S_OMEGA, ts, (size_t)M, &d_ts));
+    GF_CUDA(h, stage_in(h, S_COEF, coef, (size_t)Jc * 4, &d_coef));
+    GF_CUDA(h, stage_in(h, S_Y, alpha, (size_t)N, &d_alpha));
+    GF_CUDA(h, reserve(h, S_SCRATCH, (size_t)M * 2 * sizeof(double)));
+    Out<double> o;
+    GF_CUDA(h, stage_out(h, S_OUT, mu, (size_t)M, &o));
+    {
+        Timer timer(h);
+        GF_CUDA(h, gf::launch_cond_mean(N, d_t, M, d_ts, (int)Jc, d_coef, d_alpha,
+                                        (double *)h->buf[S_SCRATCH].p, o.dev, h->stream));
+        h->launches += 2;
     }
     GF_CUDA(h, finish_out(h, o));
     if (!(flags & GF_FLAG_ASYNC)) GF_CUDA(h, cudaStreamSynchronize(h->stream));

@@ -329,36 +329,98 @@ def _is_electron_rate(unit):
 
 
 class ConditionalDistribution:
-    """Predictive distribution at the observed times (celerite2 ``ConditionalDistribution``
-    restricted to ``t=None``: ``mean = y - diag * K^-1 (y - mu)``).  Prediction at new times and
-    predictive variances need celerite2's ``general_matmul`` operators, which are the next
-    scope row and are not built yet."""
+    """Predictive distribution of the process given observations ``y`` (celerite2
+    ``ConditionalDistribution``; reference use gadfly/gp.py:206-306, docs/gadfly/synth.rst:193-201).
+
+    * ``mean`` at the observed times is ``y - diag * K^-1 (y - mu)``; at new times ``t`` (sorted) it
+      is ``K(t, t_obs) K^-1 (y - mu)``, evaluated in O((N + M) J) on the device by
+      ``gf_conditional_mean`` (celerite2's general_matmul_lower / _upper with the kernel's
+      semiseparable coefficients) after the two O(N J) sweeps of ``apply_inverse``;
+    * ``variance`` / ``covariance`` follow celerite2: dense cross-covariances from
+      ``kernel.get_value`` on the host, solved against the stored factor by multi-right-hand-side
+      sweeps on the device (in column blocks, so that N x M never has to fit at once).
+    ``kernel`` predicts a different process than the one that was factored (e.g. one component of
+    a sum), as in celerite2."""
+
+    _BLOCK = 64      # right-hand sides per sweep launch
 
     def __init__(self, gp, y, t=None, include_mean=True, kernel=None):
-        if t is not None or kernel is not None:
-            raise NotImplementedError(
-                "prediction at new times / with a different kernel is not part of the "
-                "gadfly_b200 hot path yet (SURVEY.md section 8f-1)")
         self.gp = gp
         self.y = gp._process_input(y, require_vector=True)
         self.include_mean = include_mean
-        self._mean = None
+        self.kernel = kernel
+        if t is None:
+            self.t = None
+        else:
+            t = np.atleast_1d(np.asarray(t, dtype=np.float64))
+            if t.ndim != 1:
+                raise ValueError("The input coordinates must be one dimensional")
+            if np.any(np.diff(t) < 0.0):
+                raise ValueError("The input coordinates must be sorted")
+            self.t = np.ascontiguousarray(t)
+        self._mean = self._variance = self._covariance = None
 
+    # -- helpers -----------------------------------------------------------------------
+    def _k(self):
+        return self.gp.kernel if self.kernel is None else self.kernel
+
+    def _xs(self):
+        return self.gp._t if self.t is None else self.t
+
+    def _cross_block(self, j0, j1):
+        """K(t_obs, xs[j0:j1]) dense, and K^-1 of it."""
+        xs = self._xs()[j0:j1]
+        Kc = self._k().get_value(xs[None, :] - self.gp._t[:, None])
+        return Kc, self.gp.apply_inverse(Kc)
+
+    # -- celerite2 properties ----------------------------------------------------------
     @property
     def mean(self):
         if self._mean is None:
             gp = self.gp
             alpha = gp.apply_inverse(self.y - gp._mean_value)
-            mu = self.y - gp._diag * alpha
-            if not self.include_mean:
-                mu = mu - gp._mean_value
+            if self.t is None and self.kernel is None:
+                mu = self.y - gp._diag * alpha
+                if not self.include_mean:
+                    mu = mu - gp._mean_value
+            else:
+                xs = self._xs()
+                coef = KernelBatch([self._k()]).coef
+                mu = gp._get_solver().conditional_mean(coef, gp._t, xs, alpha)
+                if self.include_mean:
+                    mu = mu + gp._mean(xs)
             self._mean = mu
         return self._mean
 
     @property
     def variance(self):
-        raise NotImplementedError("predictive variance: SURVEY.md section 8f-1 (next scope row)")
+        if self._variance is None:
+            M = len(self._xs())
+            var = np.empty(M, dtype=np.float64)
+            k0 = float(self._k().get_value(0.0))
+            for j0 in range(0, M, self._BLOCK):
+                j1 = min(M, j0 + self._BLOCK)
+                Kc, S = self._cross_block(j0, j1)
+                var[j0:j1] = k0 - np.einsum("ij,ij->j", Kc, S)
+            self._variance = var
+        return self._variance
 
     @property
     def covariance(self):
-        raise NotImplementedError("predictive covariance: SURVEY.md section 8f-1 (next scope row)")
+        if self._covariance is None:
+            xs = self._xs()
+            M = len(xs)
+            cov = self._k().get_value(xs[:, None] - xs[None, :])
+            KxsT = self._k().get_value(xs[None, :] - self.gp._t[:, None])     # [N, M]
+            for j0 in range(0, M, self._BLOCK):
+                j1 = min(M, j0 + self._BLOCK)
+                cov[:, j0:j1] -= KxsT.T @ self.gp.apply_inverse(KxsT[:, j0:j1])
+            self._covariance = cov
+        return self._covariance
+
+    def sample(self, *, size=None, regularize=None):
+        """Draw from the predictive distribution (dense Cholesky of the covariance, as celerite2)."""
+        mu, cov = self.mean, self.covariance.copy()
+        if regularize is not None:
+            cov[np.diag_indices_from(cov)] += regularize
+        return np.random.multivariate_normal(mu, cov, size=size)

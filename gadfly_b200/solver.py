@@ -84,6 +84,9 @@ _SIGNATURES = {
     "gf_psd_batched": (ctypes.c_int, [
         ctypes.c_void_p, ctypes.c_int64, _i64p, _f64p, _f64p, _f64p, ctypes.c_int64, _f64p,
         ctypes.c_uint32]),
+    "gf_conditional_mean": (ctypes.c_int, [
+        ctypes.c_void_p, ctypes.c_int64, _f64p, ctypes.c_int64, _f64p, ctypes.c_int64, _f64p,
+        _f64p, _f64p, ctypes.c_uint32]),
 }
 
 
@@ -393,6 +396,22 @@ class Solver:
         j_off, pj = _i64(kb.j_off)
         self._check(self._lib.gf_psd_batched(
             self._h, kb.B, pj, kb.base.ctypes.data, kb.delta.ctypes.data, pw, F, po, flags))
+        return out
+
+
+    # -- K6 ----------------------------------------------------------------------------
+    def conditional_mean(self, coef, t, ts, alpha, out=None, flags=0):
+        """-> mu[M] = K(ts, t) alpha for the semiseparable kernel ``coef[Jc, 4]`` (a', b', c, d);
+        ``t`` and ``ts`` sorted ascending (celerite2 general_matmul_lower + _upper)."""
+        coef = np.ascontiguousarray(coef, dtype=np.float64).reshape(-1, 4)
+        N = int(t.numel()) if hasattr(t, "numel") else int(np.size(t))
+        M = int(ts.numel()) if hasattr(ts, "numel") else int(np.size(ts))
+        pt, k1 = _addr(t, count=N, name="t")
+        pts, k2 = _addr(ts, count=M, name="ts")
+        pa, k3 = _addr(alpha, count=N, name="alpha")
+        out, po = _out(out, (M,))
+        self._check(self._lib.gf_conditional_mean(
+            self._h, N, pt, M, pts, coef.shape[0], coef.ctypes.data, pa, po, flags))
         return out
 
 

@@ -58,6 +58,19 @@ class Term:
         ar, _, ac, _, _, _ = self.get_coefficients()
         return len(ar) + 2 * len(ac)
 
+    def get_value(self, tau):
+        """Covariance function k(tau) (celerite2 ``Term.get_value``).  Host numpy,
+        one term at a time: used for the dense cross-covariances of the predictive variance."""
+        ar, cr, ac, bc, cc, dc = self.get_coefficients()
+        tau = np.abs(np.asarray(tau, dtype=np.float64))
+        k = np.zeros_like(tau)
+        for a, c in zip(ar, cr):
+            k += a * np.exp(-c * tau)
+        for a, b, c, d in zip(ac, bc, cc, dc):
+            arg = d * tau
+            k += np.exp(-c * tau) * (a * np.cos(arg) + b * np.sin(arg))
+        return k
+
     def get_psd(self, omega):
         """Power spectral density at angular frequencies ``omega`` [rad uHz].
 
@@ -179,6 +192,43 @@ class TermConvolution(Term):
                 factor * (C1 * cos_term - C2 * sin_term),
                 factor * (C2 * cos_term + C1 * sin_term),
                 c, d)
+
+    def get_value(self, tau):
+        """Exposure-integrated covariance k_delta(tau) = delta^-2 int (delta - |x|) k(tau + x) dx
+        (celerite2 ``TermConvolution.get_value``): the semiseparable form with the
+        transformed coefficients for |tau| >= delta, the closed form of the overlapping-exposure
+        case below."""
+        ar, cr, ac, bc, cc, dc = self.term.get_coefficients()
+        dt = self.delta
+        tau = np.abs(np.asarray(tau, dtype=np.float64))
+        small = tau < dt
+        ts = tau[small]                     # overlapping exposures (usually only tau = 0)
+        dmt, dpt = dt - ts, dt + ts
+        k = np.zeros_like(tau)              # |tau| >= delta form, everywhere
+        ks = np.zeros_like(ts)
+        for a, c in zip(ar, cr):
+            cd = c * dt
+            norm = 2 * a / cd ** 2
+            k += norm * (np.cosh(cd) - 1) * np.exp(-c * tau)
+            ks += norm * (np.cosh(cd) - 1) * np.exp(-c * ts) + norm * (c * dmt - np.sinh(c * dmt))
+        for a, b, c, d in zip(ac, bc, cc, dc):
+            cd, dd = c * dt, d * dt
+            c2pd2 = c * c + d * d
+            C1 = a * (c * c - d * d) + 2 * b * c * d
+            C2 = b * (c * c - d * d) - 2 * a * c * d
+            norm = 1.0 / (dt * c2pd2) ** 2
+            cos_term = 2 * (np.cosh(cd) * np.cos(dd) - 1)
+            sin_term = 2 * (np.sinh(cd) * np.sin(dd))
+            k += ((C1 * cos_term - C2 * sin_term) * np.cos(d * tau)
+                  + (C2 * cos_term + C1 * sin_term) * np.sin(d * tau)) * (np.exp(-c * tau) * norm)
+            if ts.size:
+                k0 = np.exp(-c * ts)
+                em, ep = np.exp(-c * dmt), np.exp(-c * dpt)
+                ks += (2 * (a * c + b * d) * c2pd2 * dmt
+                       + C1 * (em * np.cos(d * dmt) + ep * np.cos(d * dpt) - 2 * k0 * np.cos(d * ts))
+                       + C2 * (em * np.sin(d * dmt) + ep * np.sin(d * dpt) - 2 * k0 * np.sin(d * ts))) * norm
+        k[small] = ks
+        return k
 
     def diagonal_correction(self):
         """k_delta(0) - sum(a'): added to the user diagonal before the scan."""

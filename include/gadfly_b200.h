@@ -130,6 +130,16 @@ int gf_psd_batched(gf_handle h, int64_t B, const int64_t *j_off, const double *c
                    const double *delta /* [B] */, const double *omega, int64_t F,
                    double *out /* [B][F] */, uint32_t flags);
 
+/* ---- K6: conditional mean at new times ------------------------------------------------
+ * Replaces celerite2 driver.general_matmul_lower + general_matmul_upper as ConditionalDistribution
+ * uses them for predict(y, t=new times) (reference gadfly/gp.py:243-306, docs/gadfly/synth.rst:193-201):
+ *   mu[i] = sum_m k(|ts[i] - t[m]|) alpha[m],  k = the semiseparable kernel of coef[Jc][4]
+ * (a', b', c, d after the exposure transform), alpha = K^-1 (y - mean) from the sweeps.
+ * t[N] and ts[M] sorted ascending; O((N + M) Jc). */
+int gf_conditional_mean(gf_handle h, int64_t N, const double *t, int64_t M, const double *ts,
+                        int64_t Jc, const double *coef, const double *alpha, double *mu,
+                        uint32_t flags);
+
 #ifdef __cplusplus
 }
 #endif

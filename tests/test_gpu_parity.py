@@ -190,6 +190,58 @@ def test_gaussian_process_api_vs_golden(solver, solar_kernel):
     assert pred.shape == gd["y"].shape
 
 
+def test_predict_at_new_times_vs_dense(solver, solar_kernel):
+    """gp.predict(y, t=new times, return_var / return_cov) -- the gap-filling call of the
+    reference's tutorial (docs/gadfly/synth.rst:193-201, gadfly/gp.py:243-306) -- against dense
+    linear algebra on the kernel definition.  The mean uses the semiseparable form of the kernel
+    for every lag (celerite2's general_matmul), the variance the exact k_delta(tau)."""
+    from oracle import dense
+    N = 300
+    t = np.arange(N) * 1.8e-4                       # 3-min cadence, exposure 1 min
+    diag = np.full(N, 20.0 ** 2)
+    base = solar_kernel.base_coefficients()
+    conv = tuple(solar_kernel.get_coefficients())
+    delta = solar_kernel.delta
+    K = dense.covariance_semiseparable(solar_kernel.scan_coefficients(), t, diag=diag)
+    rng = np.random.default_rng(8)
+    y = np.linalg.cholesky(K) @ rng.standard_normal(N)
+    alpha = np.linalg.solve(K, y)
+    ts = np.sort(np.concatenate([t[:-1] + 0.9e-4, [-5e-4, -1e-4, t[-1] + 2e-4, t[-1] + 0.5],
+                                 t[[0, 17, N - 1]], t[[40, 41]] + 2e-5]))
+    gp = g.GaussianProcess(solar_kernel, t=t, diag=diag, solver=solver)
+    mu, var = gp.predict(y, t=ts, return_var=True)
+    lag = ts[:, None] - t[None, :]
+    mu_ref = T.get_value(conv, lag) @ alpha
+    assert _maxrel(mu, mu_ref) <= RTOL
+    Ks = T.get_value_convolved(base, delta, lag.ravel()).reshape(lag.shape)
+    k0 = float(T.get_value_convolved(base, delta, np.zeros(1))[0])
+    var_ref = k0 - np.einsum("ij,ji->i", Ks, np.linalg.solve(K, Ks.T))
+    assert np.max(np.abs(var - var_ref)) <= 1e-8 * k0
+    far = var[np.searchsorted(ts, t[-1] + 0.5)]          # 5.8 days after the last observation
+    assert np.all(var > -1e-8 * k0) and 0.9 * k0 < far <= k0
+    mu2, cov = gp.predict(y, t=ts[:60], return_cov=True)
+    lag60 = ts[:60, None] - ts[None, :60]
+    cov_ref = T.get_value_convolved(base, delta, lag60.ravel()).reshape(lag60.shape) \
+        - Ks[:60] @ np.linalg.solve(K, Ks[:60].T)
+    assert np.max(np.abs(cov - cov_ref)) <= 1e-8 * k0 and _maxrel(mu2, mu_ref[:60]) <= RTOL
+    np.testing.assert_allclose(np.diag(cov), var[:60], atol=1e-8 * k0)
+    # a different kernel for the prediction: the granulation component only
+    gran = g.StellarOscillatorKernel(terms=list(solar_kernel.term.terms[:5]), delta=delta)
+    mu_g = gp.predict(y, t=ts, kernel=gran)
+    assert _maxrel(mu_g, T.get_value(tuple(gran.get_coefficients()), lag) @ alpha) <= RTOL
+    # quantities in, quantities out
+    q, qv = gp.predict(y * g.units.ppm, t=ts / 0.0864 * g.units.d, return_var=True, return_quantity=True)
+    assert q.unit == g.units.ppm and _maxrel(q.value, mu_ref) <= 1e-7
+    with pytest.raises(ValueError):
+        gp.predict(y, t=ts[::-1])
+    # observed times: unchanged celerite2 shortcut, and its variance
+    mu0, var0 = gp.predict(y, return_var=True)
+    assert _maxrel(mu0, y - diag * alpha) <= 1e-8
+    Kc = dense.covariance(base, t, delta=delta)
+    var0_ref = k0 - np.einsum("ij,ji->i", Kc, np.linalg.solve(K, Kc))
+    assert np.max(np.abs(var0 - var0_ref)) <= 1e-7 * k0
+
+
 def test_gp_not_positive_definite_raises_or_quiet(solver):
     k = g.SHOTerm(S0=1.0, w0=2.0, Q=3.0)
     t = np.array([0.0, 0.0, 1.0])
