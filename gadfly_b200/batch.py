@@ -38,7 +38,9 @@ def log_likelihood(kernels, t, y, diag=None, lengths=None, mean=0.0, quiet=True,
     """log-likelihood of B light curves under B kernels.
 
     ``t``: ``[N]`` (one cadence shared by all units), ``[B, N]``, or a flat concatenation
-    with ``lengths``;  ``y``, ``diag``: ``[B, N]`` or flat.  Non-positive-definite units give
+    with ``lengths``;  ``y``, ``diag``: ``[B, N]`` or flat -- or, with
+    ``flags=solver.FLAG_SHARED_Y``, laid out like ``t`` (one light curve for many
+    hyper-parameter sets: nothing is replicated).  Non-positive-definite units give
     ``-inf`` (``quiet=True``) or raise ``LinAlgError``."""
     from .solver import LinAlgError
     kb = _as_batch(kernels)

@@ -218,8 +218,12 @@ int run_scan(gf_handle h, int mode, int64_t B, const int64_t *n_off, const int64
     A.counter = (int *)h->buf[S_COUNTER].p;
     GF_CUDA(h, cudaMemsetAsync(A.counter, 0, sizeof(int), h->stream));
     GF_CUDA(h, stage_in(h, S_T, t, (size_t)t_len, &A.t));
-    GF_CUDA(h, stage_in(h, S_Y, y, (size_t)g.total_n, &A.y));
-    GF_CUDA(h, stage_in(h, S_DIAG, diag, (size_t)g.total_n, &A.diag));
+    const bool shared_y = (flags & GF_FLAG_SHARED_Y) != 0;
+    if (shared_y && mode != gf::MODE_LOGLIKE) return fail(h, GF_E_ARG, "GF_FLAG_SHARED_Y: log-likelihood only");
+    A.y_like_t = shared_y ? 1 : 0;
+    const size_t y_len = shared_y ? (size_t)t_len : (size_t)g.total_n;
+    GF_CUDA(h, stage_in(h, S_Y, y, y_len, &A.y));
+    GF_CUDA(h, stage_in(h, S_DIAG, diag, y_len, &A.diag));
     GF_CUDA(h, stage_in(h, S_COEF, coef, (size_t)g.total_j * 4, &A.coef));
     GF_CUDA(h, stage_in(h, S_DDIAG, ddiag, (size_t)B, &A.ddiag));
     A.seed = seed;

@@ -33,6 +33,7 @@ struct ScanArgs {
     int32_t *status;        // [B]
     uint64_t seed;
     uint64_t seq0;
+    int y_like_t;           // y / diag are addressed through t_off (shared light curve)
 };
 
 // ---------------------------------------------------------------------------------------

@@ -597,8 +597,9 @@ __device__ __forceinline__ void producer_loop(FastSmem &sm, const ScanArgs &A, c
         fast_allowed = (N > 2 * HALF) && (dmax * fmax(fabs(t[0]), fabs(t[N - 1])) < 1.0e8);
         if (lane == 0) {
             ps.t = t;
-            ps.y = A.y ? A.y + n0 : nullptr;
-            ps.dg = A.diag ? A.diag + n0 : nullptr;
+            const long long y0 = A.y_like_t ? A.t_off[b] : n0;
+            ps.y = A.y ? A.y + y0 : nullptr;
+            ps.dg = A.diag ? A.diag + y0 : nullptr;
             ps.seq = A.seq0 + (uint64_t)b;
             ps.seed = A.seed;
             ps.N = N;

@@ -63,8 +63,9 @@ __global__ void __launch_bounds__(REF_THREADS, 1) scan_ref_kernel(ScanArgs A)
         const int nb = (J + TILE - 1) / TILE;
         const int ntile = nb * (nb + 1) / 2;
         const double *t = A.t + A.t_off[b];
-        const double *y = A.y ? A.y + n0 : nullptr;
-        const double *dg = A.diag ? A.diag + n0 : nullptr;
+        const long long y0 = A.y_like_t ? A.t_off[b] : n0;
+        const double *y = A.y ? A.y + y0 : nullptr;
+        const double *dg = A.diag ? A.diag + y0 : nullptr;
         const double ddiag = A.ddiag[b];
 
         // column k = 2*term + s  (s = 0: cos column, s = 1: sin column)

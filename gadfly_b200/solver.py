@@ -31,6 +31,7 @@ __all__ = ["Solver", "KernelBatch", "SolverUnavailable", "LinAlgError", "default
 GF_MAX_J = 176
 FLAG_ASYNC = 1
 FLAG_REFERENCE_ORDER = 2
+FLAG_SHARED_Y = 4
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIBNAME = "libgadfly_b200.so"
@@ -295,8 +296,9 @@ class Solver:
         total = int(geom.n_off[-1])
         keep = []
         pt, k = _addr(t, count=geom.t_len, name="t"); keep.append(k)
-        py, k = _addr(y, count=total, name="y"); keep.append(k)
-        pd, k = _addr(diag, count=total, name="diag"); keep.append(k)
+        ny = geom.t_len if (flags & FLAG_SHARED_Y) else total     # y laid out like t
+        py, k = _addr(y, count=ny, name="y"); keep.append(k)
+        pd, k = _addr(diag, count=ny, name="diag"); keep.append(k)
         logdet, pl = _out(logdet, (B,))
         quad, pq = _out(quad, (B,))
         status, ps = _out(status, (B,), np.int32)

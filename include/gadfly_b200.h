@@ -57,6 +57,9 @@ enum {
 /* flags */
 #define GF_FLAG_ASYNC 1u          /* do not synchronise before returning */
 #define GF_FLAG_REFERENCE_ORDER 2u /* use the simple reference-order scan kernel (validation) */
+#define GF_FLAG_SHARED_Y 4u        /* y / diag (gf_loglike_batched) are laid out like t: sequence b
+                                      reads y[t_off[b] + n], so that one light curve serves many
+                                      hyper-parameter sets (stride-0 descriptor of SURVEY.md 8b) */
 
 /* ---- lifetime --------------------------------------------------------------------- */
 int gf_create(int device, gf_handle *out);

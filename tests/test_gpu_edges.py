@@ -81,3 +81,29 @@ def test_extra_terms_overdamped_and_shot_noise(solver, solar_kernel):
     assert oracle.stream(0, k3.scan_coefficients(), t, np.zeros(64))[2] == 1
     _, _, _, status = batch.log_likelihood([k3], t, np.zeros(64), solver=solver, return_parts=True)
     assert status[0] == 1
+
+
+def test_shared_light_curve_many_hyperparameter_sets(solver, solar_kernel):
+    """BASELINE configs[3] in small: one light curve, many hyper-parameter sets, y and diag passed
+    once (GF_FLAG_SHARED_Y) -- same numbers as replicating them per set."""
+    from gadfly_b200 import solver as S
+    from gadfly_b200.solver import Geometry, KernelBatch
+    N, B = 900, 7
+    rng = np.random.default_rng(21)
+    t = np.arange(N) * 6e-5
+    y = rng.standard_normal(N) * 250
+    dg = np.full(N, 15.0 ** 2)
+    kernels = [g.StellarOscillatorKernel(
+        terms=[g.SHOTerm(S0=p.S0 * f, w0=p.w0 * (2 - f), Q=p.Q) for p in solar_kernel.term.terms],
+        delta=solar_kernel.delta) for f in np.linspace(0.9, 1.1, B)]
+    kb = KernelBatch(kernels)
+    geom = Geometry.shared_t(B, N)
+    ld0, q0, s0 = solver.loglike(kb, geom, t, np.tile(y, B), np.tile(dg, B))
+    ld1, q1, s1 = solver.loglike(kb, geom, t, y, dg, flags=S.FLAG_SHARED_Y)
+    ld2, q2, s2 = solver.loglike(kb, geom, t, y, dg, flags=S.FLAG_SHARED_Y | S.FLAG_REFERENCE_ORDER)
+    assert s0.tolist() == [0] * B and s1.tolist() == [0] * B and s2.tolist() == [0] * B
+    np.testing.assert_array_equal(ld1, ld0)
+    np.testing.assert_array_equal(q1, q0)
+    np.testing.assert_allclose(ld2, ld0, rtol=RTOL)
+    np.testing.assert_allclose(q2, q0, rtol=RTOL)
+    assert np.ptp(-0.5 * (q0 + ld0)) > 1.0          # the sets really differ

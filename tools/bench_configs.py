@@ -130,18 +130,17 @@ def main():
     kb, host_s = lattice_batch(args.grid, 3)
     B, N = kb.B, 100000
     J = kb.J.astype(np.float64)
-    # one light curve for every grid point: t is shared through t_off; the C ABI addresses y through
-    # n_off (one slice per sequence), so the light curve is replicated on the device (B x 0.8 MB)
+    # one light curve for every grid point: t through t_off = 0, y through GF_FLAG_SHARED_Y
+    # (laid out like t): nothing is replicated, the 0.8 MB light curve stays L2-resident
     t = torch.arange(N, dtype=torch.float64, device=dev) * 6e-5
-    y1 = torch.randn(N, dtype=torch.float64, device=dev, generator=gen) * 285.0
+    y = torch.randn(N, dtype=torch.float64, device=dev, generator=gen) * 285.0
     try:
         logdet = torch.empty(B, dtype=torch.float64, device=dev)
         quad = torch.empty(B, dtype=torch.float64, device=dev)
         status = torch.empty(B, dtype=torch.int32, device=dev)
         geom = Geometry.shared_t(B, N)
-        y = y1.repeat(B)
         for _ in range(2):
-            solver.loglike(kb, geom, t, y, logdet=logdet, quad=quad, status=status)
+            solver.loglike(kb, geom, t, y, logdet=logdet, quad=quad, status=status, flags=S.FLAG_SHARED_Y)
         ms = solver.last_kernel_ms
         assert int(status.abs().sum()) == 0
         ll = -0.5 * (quad + logdet + N * np.log(2 * np.pi))
