@@ -199,6 +199,14 @@ __device__ __forceinline__ void mbar_wait(const uint32_t addr, const uint32_t pa
 #define GF_CTL_ASM 1
 #endif
 
+// (experiments: -DGF_DELAY_x=cycles inserts a spin at one point of a role's step, to see which
+// dependency loop sets the period -- profiles/r1_v5_role_timing_and_ab.txt)
+__device__ __forceinline__ void spin_cycles(const int cycles)
+{
+    const long long t0 = clock64();
+    while (clock64() - t0 < cycles) { }
+}
+
 __device__ __forceinline__ double shfl_xor_d(double x, int m)
 {
     return __shfl_xor_sync(0xffffffffu, x, m);
@@ -529,7 +537,13 @@ __device__ __forceinline__ int matrix_phase(FastSmem &sm, double (&S)[TILE][TILE
             sts_v2<PAR * P_PAR_BYTES>(mc.pc0 ^ (16u * q), colp[2 * q], colp[2 * q + 1]);
         }
     }
+#ifdef GF_DELAY_D
+    spin_cycles(GF_DELAY_D);
+#endif
     bar_arrive(BAR_PART + PAR, N_OPS);
+#ifdef GF_DELAY_C
+    spin_cycles(GF_DELAY_C);
+#endif
     return ctl;
 }
 
@@ -1057,8 +1071,14 @@ __device__ __forceinline__ bool chain_step(FastSmem &sm, const ScanArgs &A, Chai
             *reinterpret_cast<double2 *>(&sm.R[PAR][c.k0]) = make_double2(r2, r2);
         }
         if (c.ht == 0) sm.ctl[PAR] = ctl2;
+#ifdef GF_DELAY_B
+        spin_cycles(GF_DELAY_B);
+#endif
         ops_arrive(sm, PAR, c.lane);
     }
+#ifdef GF_DELAY_A
+    spin_cycles(GF_DELAY_A);
+#endif
 #ifdef GF_TIMING
     st.t_crit += clock64() - tc0;
 #endif
