@@ -33,8 +33,9 @@
 //      g_n + d_{n-1} alpha_n w~_{n-1} with g_n = u~_n S~(n-1) and alpha_n = u~_n . w~_{n-1}, so
 //      matrix phase n needs only w~_{n-2}: the chain work of step n-1 overlaps matrix phase n
 //      instead of serialising with it.  Likewise d_n = a_n - (u~_n S~(n-1) u~_n^T + d_{n-1}
-//      alpha_n^2).  Synchronisation is by named barriers (producer bar.arrive, consumer
-//      bar.sync) over double-buffered operands and partial sums.
+//      alpha_n^2).  Synchronisation over double-buffered operands and partial sums: named
+//      barriers (bar.arrive / bar.sync) matrix -> chain and chain <-> producer, mbarriers
+//      chain -> matrix (see mbar_wait below for why).
 #include "common.cuh"
 #ifdef GF_TIMING
 #include <cstdio>   // debug builds (tools/build_variant.sh x -DGF_TIMING): per-role cycle counts via printf
@@ -83,8 +84,8 @@ static_assert((REG_MAT - REG_LAUNCH) * MAT_THREADS <= (REG_LAUNCH - REG_HLP) * (
 constexpr double RENORM_LIMIT = 64.0;
 constexpr int RENORM_STEPS = 64;
 
-// named barriers (0 is __syncthreads)
-constexpr int BAR_OPS = 1;     // 1, 2: operands of matrix phase (n & 1) ready   [chain -> matrix]
+// named barriers (0 is __syncthreads); "operands of a matrix phase ready" [chain -> matrix] is
+// the pair of mbarriers FastSmem::mb_ops
 constexpr int BAR_PART = 3;    // 3, 4: partial sums of matrix phase ready       [matrix -> chain]
 constexpr int BAR_CH = 5;      // chain-warp internal
 constexpr int BAR_FULL = 6;    // 6, 7: ring half produced                       [producer -> chain]
@@ -151,11 +152,7 @@ __device__ __forceinline__ void bar_arrive(int id, int count)
 // The hand-over chain -> matrix uses mbarriers instead of a named barrier: a named barrier would
 // also synchronise the eight matrix warps with each other at every phase (the fastest waits for the
 // slowest: measured 250 cycles per step), an mbarrier lets each matrix warp run at its own pace --
-// the two matrix warps of a scheduler drift apart, so that one warp's latency-bound prologue and
-// epilogue overlap the other's DFMA stream.
-#ifndef GF_OPS_MBAR
-#define GF_OPS_MBAR 1
-#endif
+// (measured: 2226 -> 1930 cycles per step).
 __device__ __forceinline__ void mbar_init(const uint32_t addr, const int count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
@@ -190,21 +187,6 @@ __device__ __forceinline__ void mbar_wait(const uint32_t addr, const uint32_t pa
         "bra.uni GF_MBAR_WAIT;\n"
         "GF_MBAR_DONE:\n"
         "}\n" ::"r"(addr), "r"(parity) : "memory");
-}
-
-#ifndef GF_EARLY_TEST
-#define GF_EARLY_TEST 1
-#endif
-#ifndef GF_CTL_ASM
-#define GF_CTL_ASM 1
-#endif
-
-// (experiments: -DGF_DELAY_x=cycles inserts a spin at one point of a role's step, to see which
-// dependency loop sets the period -- profiles/r1_v5_role_timing_and_ab.txt)
-__device__ __forceinline__ void spin_cycles(const int cycles)
-{
-    const long long t0 = clock64();
-    while (clock64() - t0 < cycles) { }
 }
 
 __device__ __forceinline__ double shfl_xor_d(double x, int m)
@@ -342,15 +324,11 @@ __device__ __forceinline__ double2 mat_col_op(const MatConst &mc)
     return ((J < 4) ? mc.c_lo : mc.c_hi)[PAR * TILE * NB_PAD + (J & 3) * NB_PAD];
 }
 
-#ifndef GF_RP_TAIL
-#define GF_RP_TAIL 1
-#endif
 template <int I>
 __device__ __forceinline__ void matrix_row_pair(const double2 a0, const double2 a1, double (&S)[TILE][TILE],
                                                 const double (&uj)[TILE], const double (&wj)[TILE],
                                                 double (&rowp)[TILE], double (&colp)[TILE])
 {
-#if GF_RP_TAIL
     // update and column sums only: 16 independent updates, then 8 chains of depth 2
     (void)uj; (void)rowp;
     double T0[TILE], T1[TILE];
@@ -362,20 +340,6 @@ __device__ __forceinline__ void matrix_row_pair(const double2 a0, const double2 
     for (int j = 0; j < TILE; ++j) { S[I][j] = T0[j]; colp[j] = fma(a0.x, T0[j], colp[j]); }
 #pragma unroll
     for (int j = 0; j < TILE; ++j) { S[I + 1][j] = T1[j]; colp[j] = fma(a1.x, T1[j], colp[j]); }
-#else
-    double rp0 = 0.0, rp1 = 0.0;
-#pragma unroll
-    for (int j = 0; j < TILE; ++j) {
-        const double T0 = fma(a0.y, wj[j], S[I][j]);
-        const double T1 = fma(a1.y, wj[j], S[I + 1][j]);
-        S[I][j] = T0; S[I + 1][j] = T1;
-        colp[j] = fma(a0.x, T0, colp[j]);
-        rp0 = fma(T0, uj[j], rp0);
-        colp[j] = fma(a1.x, T1, colp[j]);
-        rp1 = fma(T1, uj[j], rp1);
-    }
-    rowp[I] = rp0; rowp[I + 1] = rp1;
-#endif
 }
 
 // Row sums of the updated tile, after the update: 16 independent chains of depth 4 (every row in
@@ -438,24 +402,17 @@ __device__ __forceinline__ int matrix_phase(FastSmem &sm, double (&S)[TILE][TILE
 #ifdef GF_TIMING
     const long long tw0 = clock64();
 #endif
-#if GF_OPS_MBAR
     // `ready`: the test issued in the previous phase (its latency hidden there) already saw the
     // operands of this phase
     if (!ready) mbar_wait((uint32_t)__cvta_generic_to_shared(&sm.mb_ops[PAR]), use & 1u);
-#else
-    (void)use;
-    bar_sync(BAR_OPS + PAR, N_OPS);
-#endif
 #ifdef GF_TIMING
     g_wait += clock64() - tw0;
     g_notready += ready ? 0 : 1;
 #endif
     // control word: loaded through a per-thread address so that the test is an ordinary predicate
     // (the uniform-datapath form costs an R2UR round trip in front of the DFMA stream)
-#if GF_CTL_ASM
     int ctl;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ctl) : "r"(mc.ctl0 + PAR * 4u) : "memory");
-#endif
     double uj[TILE], wj[TILE];
     {
         double2 c;
@@ -468,9 +425,6 @@ __device__ __forceinline__ int matrix_phase(FastSmem &sm, double (&S)[TILE][TILE
         c = mat_col_op<PAR, 6>(mc); uj[6] = c.x; wj[6] = c.y;
         c = mat_col_op<PAR, 7>(mc); uj[7] = c.x; wj[7] = c.y;
     }
-#if !GF_CTL_ASM
-    const int ctl = sm.ctl[PAR];
-#endif
     if (ctl) {
         if (ctl & CTL_STOP) return ctl;
         matrix_renorm<PAR>(sm, S, mc.geom, wj);
@@ -485,9 +439,7 @@ __device__ __forceinline__ int matrix_phase(FastSmem &sm, double (&S)[TILE][TILE
     matrix_row_pair<2>(mat_row_op<PAR, 2>(mc), mat_row_op<PAR, 3>(mc), S, uj, wj, rowp, colp);
     matrix_row_pair<4>(mat_row_op<PAR, 4>(mc), mat_row_op<PAR, 5>(mc), S, uj, wj, rowp, colp);
     matrix_row_pair<6>(mat_row_op<PAR, 6>(mc), mat_row_op<PAR, 7>(mc), S, uj, wj, rowp, colp);
-#if GF_RP_TAIL
     matrix_row_sums(S, uj, rowp);
-#endif
 
     // quadratic form u~ S~ u~^T: this tile's share, reduced over the warp
     double qf0 = colp[0] * uj[0], qf1 = colp[1] * uj[1];
@@ -495,12 +447,10 @@ __device__ __forceinline__ int matrix_phase(FastSmem &sm, double (&S)[TILE][TILE
     for (int j = 2; j < TILE; j += 2) { qf0 = fma(colp[j], uj[j], qf0); qf1 = fma(colp[j + 1], uj[j + 1], qf1); }
     double qf = (qf0 + qf1) * mc.qw;
 
-#if GF_OPS_MBAR && GF_EARLY_TEST
     // are the operands of the next phase there already?  (normally yes: asked here, used at the top
     // of the next phase)
     ready = last ? false
                  : mbar_test((uint32_t)__cvta_generic_to_shared(&sm.mb_ops[PAR ^ 1]), (use + PAR) & 1u);
-#endif
     // 2x2 group: combine the two tiles of a block row (lane ^ 1) and of a block column (lane ^ 2)
     // (each lane keeps four of the eight sums: rows 4 cj.., columns 4 ri..)
     const bool hr = geom_mr(mc.geom) != 0, hc = geom_mc(mc.geom) != 0;
@@ -537,13 +487,7 @@ __device__ __forceinline__ int matrix_phase(FastSmem &sm, double (&S)[TILE][TILE
             sts_v2<PAR * P_PAR_BYTES>(mc.pc0 ^ (16u * q), colp[2 * q], colp[2 * q + 1]);
         }
     }
-#ifdef GF_DELAY_D
-    spin_cycles(GF_DELAY_D);
-#endif
     bar_arrive(BAR_PART + PAR, N_OPS);
-#ifdef GF_DELAY_C
-    spin_cycles(GF_DELAY_C);
-#endif
     return ctl;
 }
 
@@ -890,24 +834,13 @@ __device__ __forceinline__ void producer_loop(FastSmem &sm, const ScanArgs &A, c
 // 1 / d for a positive normal d, branch-free: hardware seed (>= 20 bits) and one third-order step
 // x (1 + e + e^2), e = 1 - d x (relative error e^3 < 2^-60; three dependent DFMA instead of the
 // four of two Newton steps -- this sits on the chain's serial path)
-#ifndef GF_RCP3
-#define GF_RCP3 1
-#endif
 __device__ __forceinline__ double fast_rcp(double d)
 {
     double x;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
-#if GF_RCP3
     const double e = fma(-d, x, 1.0);
     const double p = fma(e, e, e);
     return fma(x, p, x);
-#else
-    double e = fma(-d, x, 1.0);
-    x = fma(x, e, x);
-    e = fma(-d, x, 1.0);
-    x = fma(x, e, x);
-    return x;
-#endif
 }
 
 // Sum (a, b) over the three chain warps, in two parts so that independent work can be placed
@@ -937,13 +870,8 @@ __device__ __forceinline__ void chain_reduce2_cta(FastSmem &sm, int hw, int lane
 // chain -> matrix: the operands of a matrix phase of parity par are in shared memory
 __device__ __forceinline__ void ops_arrive(FastSmem &sm, const int par, const int lane)
 {
-#if GF_OPS_MBAR
     __syncwarp();
     if (lane == 0) mbar_arrive((uint32_t)__cvta_generic_to_shared(&sm.mb_ops[par]));
-#else
-    (void)sm; (void)lane;
-    bar_arrive(BAR_OPS + par, N_OPS);
-#endif
 }
 
 // State the chain carries from step to step.  The serial path of the recurrence is kept as short
@@ -1071,14 +999,8 @@ __device__ __forceinline__ bool chain_step(FastSmem &sm, const ScanArgs &A, Chai
             *reinterpret_cast<double2 *>(&sm.R[PAR][c.k0]) = make_double2(r2, r2);
         }
         if (c.ht == 0) sm.ctl[PAR] = ctl2;
-#ifdef GF_DELAY_B
-        spin_cycles(GF_DELAY_B);
-#endif
         ops_arrive(sm, PAR, c.lane);
     }
-#ifdef GF_DELAY_A
-    spin_cycles(GF_DELAY_A);
-#endif
 #ifdef GF_TIMING
     st.t_crit += clock64() - tc0;
 #endif
@@ -1203,14 +1125,12 @@ __device__ __forceinline__ bool next_sequence(FastSmem &sm, const ScanArgs &A, c
     __syncthreads();   // everybody is done with the previous sequence
     if (tid == 0) {
         sm.next = atomicAdd(A.counter, 1);
-#if GF_OPS_MBAR
         // one arrival per chain warp; the phase parities restart with every sequence
         for (int p = 0; p < 2; ++p) {
             const uint32_t mb = (uint32_t)__cvta_generic_to_shared(&sm.mb_ops[p]);
             if (!q.first) mbar_inval(mb);
             mbar_init(mb, CH_THREADS / 32);
         }
-#endif
     }
     q.first = false;
     // operand buffers (padding columns must read as zero) and partial sums
