@@ -388,6 +388,15 @@ __device__ __forceinline__ void matrix_renorm(FastSmem &sm, double (&S)[TILE][TI
 #define g_wait tm_wait
 #define g_notready tm_notready
 #endif
+#ifdef GF_TIMING
+// clock read that cannot be scheduled before `v` is available
+__device__ __forceinline__ long long clk_after(const double v)
+{
+    long long t;
+    asm volatile("{\n.reg .f64 dd;\nmov.f64 dd, %1;\nmov.u64 %0, %%clock64;\n}\n" : "=l"(t) : "d"(v) : "memory");
+    return t;
+}
+#endif
 // One phase of a matrix thread: wait for the operands, (renormalisation,) the arithmetic, the
 // exchange inside the 2x2 group, the warp reduction of the quadratic form, stores and hand-over.
 template <int PAR>
@@ -889,7 +898,7 @@ struct ChainState {
     double zp;              // y_{n-1} (log-likelihood) or sqrt(d_{n-1}) n_{n-1} (sampling)
     double logdet, prod, quad;
 #ifdef GF_TIMING
-    long long t_part = 0, t_crit = 0;
+    long long t_part = 0, t_crit = 0, t_seg[4] = {0, 0, 0, 0};
 #endif
 };
 
@@ -948,6 +957,26 @@ __device__ __forceinline__ bool chain_step(FastSmem &sm, const ScanArgs &A, Chai
     st.t_part += clock64() - tp0;
     const long long tc0 = clock64();
 #endif
+    // pivot d_n = a_n - (u~ S~(n-1) u~^T + alpha_n tau_n) and its reciprocal first: scalars of the
+    // previous step and four loads, nothing of the g sum -- and no branch: a non-positive pivot
+    // rides along as CTL_STOP in the hand-over and is reported after it, so that the whole section
+    // up to the hand-over is one basic block and this chain overlaps the g sum and the butterfly
+    double qf;
+    {
+        const double2 *Q2 = reinterpret_cast<const double2 *>(&sm.QF[PAR][0]);
+        constexpr int NQ = MAT_WARPS * QF_PER_WARP / 2;
+        double2 q[NQ];
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) q[i] = Q2[i];
+#pragma unroll
+        for (int w = NQ / 2; w >= 1; w >>= 1)
+#pragma unroll
+            for (int i = 0; i < w; ++i) { q[i].x += q[i + w].x; q[i].y += q[i + w].y; }
+        qf = q[0].x + q[0].y;
+    }
+    const double dn = ra - fma(st.alpha, st.tau, qf);
+    const bool ok = dn > 0.0;
+    const double rd = fast_rcp(dn);
     // g_n: unused slots hold zeros, so the sum always runs over all of them (two batches of six
     // slots to keep the register footprint of the loads small)
     static_assert(NSLOT == 12, "summation tree below is written for 12 slots");
@@ -964,30 +993,22 @@ __device__ __forceinline__ bool chain_step(FastSmem &sm, const ScanArgs &A, Chai
         gc = gc0 + (((v[0].x + v[1].x) + (v[2].x + v[3].x)) + (v[4].x + v[5].x));
         gs = gs0 + (((v[0].y + v[1].y) + (v[2].y + v[3].y)) + (v[4].y + v[5].y));
     }
+#ifdef GF_TIMING
+    st.t_seg[0] += clk_after(gc + gs) - tc0;                 // PART -> g
+#endif
     // t~_n = v~_n - (g_n + alpha_n t~_{n-1}), then into the frame of step n + 1
     const double tc = vn.x - fma(st.alpha, st.tc, gc), ts = vn.y - fma(st.alpha, st.ts, gs);
     const double tc1 = tc * r1, ts1 = ts * r1;
     // the serial path: tau_{n+1} = u~_{n+1} . t~_n (with gamma_n riding along)
     const double tpart = c.act ? fma(u1.x, tc1, u1.y * ts1) : 0.0;
     const double red = chain_reduce2_warp(c.lane, tpart, gpart);
+#ifdef GF_TIMING
+    st.t_seg[1] += clk_after(red) - tc0;                     // -> warp butterfly done
+#endif
 
-    // pivot, beside the reduction: d_n = a_n - (u~ S~(n-1) u~^T + alpha_n tau_n)
-    double qf;
-    {
-        const double2 *Q2 = reinterpret_cast<const double2 *>(&sm.QF[PAR][0]);
-        constexpr int NQ = MAT_WARPS * QF_PER_WARP / 2;
-        double2 q[NQ];
-#pragma unroll
-        for (int i = 0; i < NQ; ++i) q[i] = Q2[i];
-#pragma unroll
-        for (int w = NQ / 2; w >= 1; w >>= 1)
-#pragma unroll
-            for (int i = 0; i < w; ++i) { q[i].x += q[i + w].x; q[i].y += q[i + w].y; }
-        qf = q[0].x + q[0].y;
-    }
-    const double dn = ra - fma(st.alpha, st.tau, qf);
-    if (!(dn > 0.0)) return false;
-    const double rd = fast_rcp(dn);
+#ifdef GF_TIMING
+    st.t_seg[2] += clk_after(rd) - tc0;                      // -> reciprocal of the pivot
+#endif
     const double wc1 = tc1 * rd, ws1 = ts1 * rd;            // w~_n, frame of step n + 1
     // operands of matrix phase n + 2: row n + 2 and the rank-1 term of step n
     if (n + 2 < c.N) {
@@ -998,15 +1019,19 @@ __device__ __forceinline__ bool chain_step(FastSmem &sm, const ScanArgs &A, Chai
             sm.C[PAR][c.ke + 1][c.kb] = make_double2(u2.y, ws1);
             *reinterpret_cast<double2 *>(&sm.R[PAR][c.k0]) = make_double2(r2, r2);
         }
-        if (c.ht == 0) sm.ctl[PAR] = ctl2;
+        if (c.ht == 0) sm.ctl[PAR] = ok ? ctl2 : CTL_STOP;
         ops_arrive(sm, PAR, c.lane);
     }
 #ifdef GF_TIMING
     st.t_crit += clock64() - tc0;
 #endif
+    if (!ok) return false;
     // ---- off the matrix' critical path --------------------------------------------------------
     double tau, gamma;
     chain_reduce2_cta<PAR>(sm, c.hw, c.lane, red, tau, gamma);
+#ifdef GF_TIMING
+    st.t_seg[3] += clk_after(tau + gamma) - tc0;             // -> cross-warp sum
+#endif
     if (MODE == MODE_FACTOR) {
         if (A.out_W && c.act) {
             const double qn = sm.Rq[s0][tix];
@@ -1080,8 +1105,7 @@ __device__ __forceinline__ void chain_loop(FastSmem &sm, const ScanArgs &A, cons
                 // hand-shake with the producer going until the natural end
                 const int par = n & 1;
                 fail = n + 1;
-                if (ht == 0) { sm.stop = n + 2; sm.ctl[par] = CTL_STOP; }
-                if (n + 2 < N) ops_arrive(sm, par, c.lane);
+                if (ht == 0) sm.stop = n + 2;       // (the step itself handed CTL_STOP over)
                 if (n + 1 < N) bar_sync(BAR_PART + (par ^ 1), N_OPS);
                 drain = true;
             }
@@ -1101,8 +1125,9 @@ __device__ __forceinline__ void chain_loop(FastSmem &sm, const ScanArgs &A, cons
     }
 #ifdef GF_TIMING
     if (blockIdx.x == 0 && c.lane == 0)
-        printf("chain warp %d: PART wait %.1f cyc/step, critical section %.1f cyc/step\n", c.hw,
-               (double)st.t_part / N, (double)st.t_crit / N);
+        printf("chain warp %d: PART wait %.1f, from PART: g %.0f, warp butterfly %.0f, 1/d %.0f, hand-over %.0f, "
+               "cross-warp sum %.0f cycles/step\n", c.hw, (double)st.t_part / N, (double)st.t_seg[0] / N,
+               (double)st.t_seg[1] / N, (double)st.t_seg[2] / N, (double)st.t_crit / N, (double)st.t_seg[3] / N);
 #endif
     if (ht == 0) {
         if (st.prod != 1.0) st.logdet += log(st.prod);
