@@ -288,16 +288,16 @@ def run_b200(args):
             pass
         hbm_achieved = 24.0 * B * N / (dom_ms * 1e-3) / 1e9
         # DRAM traffic of one launch: bytes per point from the committed ncu capture of the same
-        # kernel (profiles/r1_v5_traffic.json) x the points of this launch
+        # kernel (profiles/r1_v6_traffic.json) x the points of this launch
         traffic, traffic_src = None, None
         try:
-            with open(os.path.join(ROOT, "profiles", "r1_v5_traffic.json")) as fh:
+            with open(os.path.join(ROOT, "profiles", "r1_v6_traffic.json")) as fh:
                 tj = json.load(fh)
             for name in (f"scan ({dom})", "scan (loglike)"):
                 if name in tj:
                     per_point = (tj[name]["dram_bytes_read"] + tj[name]["dram_bytes_write"]) / tj["points_per_launch"]
                     traffic = per_point * B * N
-                    traffic_src = f"{name}: {per_point:.2f} B/point measured by ncu (profiles/r1_v5_traffic.json)"
+                    traffic_src = f"{name}: {per_point:.2f} B/point measured by ncu (profiles/r1_v6_traffic.json)"
                     break
         except Exception:
             pass
