@@ -194,36 +194,6 @@ __device__ __forceinline__ double shfl_xor_d(double x, int m)
     return __shfl_xor_sync(0xffffffffu, x, m);
 }
 
-// sin and cos of a double that is already the rounded phase d * t: three-constant Cody-Waite
-// reduction with FMA (absolute error of the reduced argument ~2e-16 for |x| < 2^30) and the
-// fdlibm kernel polynomials on [-pi/4, pi/4].  No slow path, no local memory.
-__device__ __forceinline__ void sincos_cw(double x, double *sn, double *cs)
-{
-    if (!(fabs(x) < 1.0e9)) { sincos(x, sn, cs); return; }
-    const double kd = rint(x * 0.6366197723675814);
-    const int q = (int)kd;
-    double r = fma(-kd, 1.5707963267948966, x);
-    r = fma(-kd, 6.123233995736766e-17, r);
-    r = fma(-kd, -1.4973849048591698e-33, r);
-    const double z = r * r;
-    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
-    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
-    ps = fma(ps, z, 2.75573137070700676789e-06);
-    pc = fma(pc, z, -2.75573143513906633035e-07);
-    ps = fma(ps, z, -1.98412698298579493134e-04);
-    pc = fma(pc, z, 2.48015872894767294178e-05);
-    ps = fma(ps, z, 8.33333333332248946124e-03);
-    pc = fma(pc, z, -1.38888888888741095749e-03);
-    ps = fma(ps, z, -1.66666666666666324348e-01);
-    pc = fma(pc, z, 4.16666666666666019037e-02);
-    const double s = fma(ps * z, r, r);
-    const double c = fma(z * z, pc, fma(-0.5, z, 1.0));
-    const double s1 = (q & 1) ? c : s;
-    const double c1 = (q & 1) ? s : c;
-    *sn = (q & 2) ? -s1 : s1;
-    *cs = ((q + 1) & 2) ? -c1 : c1;
-}
-
 // ------------------------------------------------------------------------------------------
 // matrix warpgroups
 // ------------------------------------------------------------------------------------------

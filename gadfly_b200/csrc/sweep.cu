@@ -9,7 +9,9 @@
 // One CTA per sequence, one thread per complex term (cos and sin columns).  The sweep is a
 // length-N dependency chain, so the kernel works in chunks of CH steps: the chunk's rows
 // (sincos, exp) and the W / t / y loads of the NEXT chunk are independent of the chain and
-// overlap with it; per step the chain is one FMA pair, a warp-shuffle sum and one barrier.
+// overlap with it; per step the solve chain is one FMA pair, a warp-shuffle sum and one barrier.
+// The matmul ops have no feedback from the outputs into the state: their CH dot products per
+// chunk are reduced together (one halving butterfly, one barrier per chunk).
 #include "common.cuh"
 
 namespace gf {
@@ -36,6 +38,7 @@ sweep_kernel(int64_t B, const int64_t *__restrict__ n_off, const int64_t *__rest
 {
     __shared__ double s_red[2][SW_WARPS];
     __shared__ double s_y[2];
+    __shared__ double s_chunk[2][SW_WARPS][CH];     // matmul: the CH sums of a chunk per warp
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
 
@@ -71,15 +74,81 @@ sweep_kernel(int64_t B, const int64_t *__restrict__ n_off, const int64_t *__rest
                 tt[k] = ok ? t[n] : 0.0;
                 wc[k] = (ok && act) ? W[n * J + tid] : 0.0;
                 ws[k] = (ok && act) ? W[n * J + Jc + tid] : 0.0;
-                yy[k] = (ok && tid == 0) ? Y[n] : 0.0;
+                yy[k] = (ok && (tid == 0 || !SOLVE)) ? Y[n] : 0.0;    // matmul: every thread needs y
             }
 #pragma unroll
             for (int k = 0; k < CH; ++k) {
                 double sn, cs;
-                sincos(cd * tt[k], &sn, &cs);
+                sincos_cw(cd * tt[k], &sn, &cs);
                 uc[k] = ca * cs + cb * sn;
                 us[k] = ca * sn - cb * cs;
             }
+            // decay over each step of the chunk (UPPER: t_n - t_{n+1}; lower: t_{n-1} - t_n; both <= 0):
+            // off the chain as well
+            double pk[CH];
+#pragma unroll
+            for (int k = 0; k < CH; ++k) {
+                const double tp = (k == 0) ? t_nb : tt[k - 1];
+                pk[k] = (base + k > 0 && base + k < N) ? exp(cc * (UPPER ? (tt[k] - tp) : (tp - tt[k]))) : 0.0;
+            }
+            if (!SOLVE) {
+                // matmul: the state does not depend on the outputs, so the CH dot products of the
+                // chunk are independent -- one multi-value butterfly and one barrier per chunk
+                double part[CH];
+#pragma unroll
+                for (int k = 0; k < CH; ++k) {
+                    if (base + k > 0) {
+                        const double pr = (k == 0) ? prev : yy[k - 1];
+                        const double a0 = (k == 0) ? (UPPER ? uc_nb : wc_nb) : (UPPER ? uc[k - 1] : wc[k - 1]);
+                        const double a1 = (k == 0) ? (UPPER ? us_nb : ws_nb) : (UPPER ? us[k - 1] : ws[k - 1]);
+                        Fc = pk[k] * fma(a0, pr, Fc);
+                        Fs = pk[k] * fma(a1, pr, Fs);
+                    }
+                    part[k] = UPPER ? (wc[k] * Fc + ws[k] * Fs) : (uc[k] * Fc + us[k] * Fs);
+                }
+                // halving butterfly: after the stages 16, 8, 4 every lane holds one of the CH = 8 sums
+                // (index = lane bits 4..2), then two plain stages
+                {
+                    const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0, h4 = (lane & 4) != 0;
+                    double q4[4], q2[2], q1;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const double send = h16 ? part[i] : part[4 + i], keep = h16 ? part[4 + i] : part[i];
+                        q4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const double send = h8 ? q4[i] : q4[2 + i], keep = h8 ? q4[2 + i] : q4[i];
+                        q2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                    }
+                    {
+                        const double send = h4 ? q2[0] : q2[1], keep = h4 ? q2[1] : q2[0];
+                        q1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                    }
+                    q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
+                    q1 += __shfl_xor_sync(0xffffffffu, q1, 1);
+                    // value index held by this lane: bit 2 of k from lane bit 4, bit 1 from bit 3, bit 0 from bit 2
+                    const int kidx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+                    const int par = (int)((base / CH) & 1);
+                    if ((lane & 3) == 0) s_chunk[par][warp][kidx] = q1;
+                    __syncthreads();
+                    if (tid < CH && base + tid < N) {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int w = 0; w < SW_WARPS; ++w) acc += s_chunk[par][w][tid];
+                        const int64_t n = UPPER ? (N - 1 - (base + tid)) : (base + tid);
+                        Z[n] = Y[n] + acc;
+                    }
+                }
+                // carry the neighbour row into the next chunk
+                const int last = (int)((N - base < CH ? N - base : CH) - 1);
+#pragma unroll
+                for (int k = 0; k < CH; ++k)
+                    if (k == last) {
+                        prev = yy[k];
+                        uc_nb = uc[k]; us_nb = us[k]; wc_nb = wc[k]; ws_nb = ws[k]; t_nb = tt[k];
+                    }
+            } else {
 #pragma unroll
             for (int k = 0; k < CH; ++k) {
                 const int64_t m = base + k;
@@ -87,8 +156,7 @@ sweep_kernel(int64_t B, const int64_t *__restrict__ n_off, const int64_t *__rest
                 const int64_t n = UPPER ? (N - 1 - m) : m;
                 const int par = (int)(m & 1);
                 if (m > 0) {
-                    // UPPER: t_n - t_{n+1}; lower: t_{n-1} - t_n  (both <= 0)
-                    const double p = exp(cc * (UPPER ? (tt[k] - t_nb) : (t_nb - tt[k])));
+                    const double p = pk[k];
                     if (UPPER) { Fc = p * (Fc + uc_nb * prev); Fs = p * (Fs + us_nb * prev); }
                     else       { Fc = p * (Fc + wc_nb * prev); Fs = p * (Fs + ws_nb * prev); }
                 }
@@ -101,10 +169,11 @@ sweep_kernel(int64_t B, const int64_t *__restrict__ n_off, const int64_t *__rest
 #pragma unroll
                 for (int w = 0; w < SW_WARPS; ++w) acc += s_red[par][w];
                 const double yn = s_y[par];
-                const double zn = SOLVE ? (yn - acc) : (yn + acc);
+                const double zn = yn - acc;
                 if (tid == 0) Z[n] = zn;
-                prev = SOLVE ? zn : yn;
+                prev = zn;
                 uc_nb = uc[k]; us_nb = us[k]; wc_nb = wc[k]; ws_nb = ws[k]; t_nb = tt[k];
+            }
             }
         }
         __syncthreads();
