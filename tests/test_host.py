@@ -238,3 +238,25 @@ def test_batched_feeder_matches_per_star():
     kb2 = KernelBatch.for_stars(M, R, T, L, alpha=2.0)
     gran = slice(0, 5)
     np.testing.assert_allclose(kb2.base[gran, 0], 2.0 * kb.base[gran, 0], rtol=1e-13)
+
+
+def test_get_value_matches_oracle_and_defining_integral(solar_kernel):
+    """Term.get_value / TermConvolution.get_value (celerite2 API used by the predictive variance):
+    both branches of the exposure-integrated kernel against the oracle, k(0) against the scan's
+    diagonal, and one overlapping-exposure lag against the defining integral."""
+    from oracle import dense
+    base = solar_kernel.base_coefficients()
+    delta = solar_kernel.delta
+    tau = np.concatenate([np.linspace(0.0, 0.99 * delta, 7), [delta], np.linspace(1.01 * delta, 0.3, 40)])
+    got = solar_kernel.get_value(tau)
+    np.testing.assert_allclose(got, T.get_value_convolved(base, delta, tau), rtol=1e-10)
+    np.testing.assert_allclose(solar_kernel.get_value(-tau), got, rtol=0)           # even in tau
+    scan = solar_kernel.scan_coefficients()
+    assert got[0] == pytest.approx(np.sum(scan[2]) + scan[6], rel=1e-8)               # k(0) = sum a' + ddiag
+    assert solar_kernel.get_value(0.4 * delta) == pytest.approx(
+        float(dense.exposure_integral(base, delta, 0.4 * delta)), rel=1e-7)
+    plain = solar_kernel.term
+    np.testing.assert_allclose(plain.get_value(tau), T.get_value(plain.base_coefficients(), tau), rtol=1e-13)
+    over = g.SHOTerm(S0=3.0, w0=2.0, Q=0.3)                                          # real terms
+    np.testing.assert_allclose(over.get_value(tau), T.get_value(over.base_coefficients(), tau), rtol=1e-13)
+    assert solar_kernel.get_value(np.zeros((2, 3))).shape == (2, 3)
