@@ -107,3 +107,23 @@ def test_shared_light_curve_many_hyperparameter_sets(solver, solar_kernel):
     np.testing.assert_allclose(ld2, ld0, rtol=RTOL)
     np.testing.assert_allclose(q2, q0, rtol=RTOL)
     assert np.ptp(-0.5 * (q0 + ld0)) > 1.0          # the sets really differ
+
+
+def test_full_length_light_curve(solver, solar_kernel):
+    """BASELINE's full sequence length: 2^20 points of 1-min cadence (728 days), fused Philox
+    sample and fused log-likelihood against the CPU oracle on the same inputs -- 1M steps of
+    lazy-decay frames, producer tables and renormalisations without drift."""
+    from gadfly_b200 import philox
+    N = 1 << 20
+    t = np.arange(N) * 6e-5
+    scan = solar_kernel.scan_coefficients()
+    x, status = batch.sample([solar_kernel], t, seed=5, solver=solver, subtract_mean=False)
+    nrm = philox.normals(5, 0, N)
+    x_ref, ld_ref, st_ref = oracle.stream(1, scan, t, nrm, fast=True)
+    assert status[0] == 0 and st_ref == 0
+    assert _maxrel(x[0], x_ref) <= RTOL
+    ll, logdet, quad, status = batch.log_likelihood([solar_kernel], t, x_ref, solver=solver, return_parts=True)
+    o_ld, o_q, _ = oracle.stream(0, scan, t, x_ref, fast=True)
+    assert status[0] == 0
+    assert logdet[0] == pytest.approx(o_ld, rel=RTOL) and quad[0] == pytest.approx(o_q, rel=RTOL)
+    assert quad[0] == pytest.approx(np.sum(nrm * nrm), rel=1e-8)       # |L^-1 L n|^2 = |n|^2
