@@ -18,6 +18,18 @@ namespace gf {
 
 namespace {
 
+// 1 / x for a positive normal x to ~1 ulp: hardware seed (>= 20 bits) and one third-order step.
+// (The IEEE division of __ddiv_rn costs ~25 FP64 instructions per (term, bin) and dominated the
+// kernel; the quotient is not cancellation-sensitive, the 1e-12 bar needs 1e-15, not 0.5 ulp.)
+__device__ __forceinline__ double psd_rcp(const double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double e = fma(-x, r, 1.0);
+    const double p = fma(e, e, e);
+    return fma(r, p, r);
+}
+
 constexpr int PSD_THREADS = 256;
 constexpr int PSD_BPT = 4;           // bins per thread
 constexpr int PSD_MAX_TERMS = 512;   // terms staged per pass
@@ -67,7 +79,7 @@ psd_kernel(const int64_t *__restrict__ j_off, const double *__restrict__ coef,
             for (int q = 0; q < PSD_BPT; ++q) {
                 const double num = __dadd_rn(k.z, __dmul_rn(k.w, w2[q]));
                 const double den = __dadd_rn(__dadd_rn(w4[q], __dmul_rn(k.x, w2[q])), k.y);
-                acc[q] = __dadd_rn(acc[q], __ddiv_rn(num, den));
+                acc[q] = __dadd_rn(acc[q], __dmul_rn(num, psd_rcp(den)));
             }
         }
     }
