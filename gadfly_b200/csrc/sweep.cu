@@ -6,21 +6,19 @@
 // with prev = z (solve) or y (matmul) of the neighbouring step and p_n the decay over the
 // step.  U rows are regenerated from (t, coef); W is read once, coalesced.
 //
-// One CTA per sequence, one thread per complex term (cos and sin columns).  The sweep is a
-// length-N dependency chain, so the kernel works in chunks of CH steps: the chunk's rows
-// (sincos, exp) and the W / t / y loads of the NEXT chunk are independent of the chain and
-// overlap with it; per step the solve chain is one FMA pair, a warp-shuffle sum and one barrier.
-// The matmul ops have no feedback from the outputs into the state: their CH dot products per
-// chunk are reduced together (one halving butterfly, one barrier per chunk).
+// One CTA per sequence.  The dependency chain of a sweep is one FMA pair, one dot product and its
+// reduction per step; regenerating the U rows (sincos, exp: ~85 FP64 instructions per term and
+// step) in the same threads would triple the step.  So SW2_PROD producer warps generate the rows
+// of the coming steps into a shared-memory ring (each warp a step of its own, three terms per
+// lane), and ONE chain warp holds the whole state F (three terms per lane): the dot product is a
+// single warp butterfly -- no cross-warp stage, no __syncthreads on the chain.  Hand-over by
+// mbarriers per ring half (8 steps): full[h] (one arrival per step's producer warp), empty[h]
+// (one arrival of the chain).
 #include "common.cuh"
 
 namespace gf {
 
 namespace {
-
-constexpr int SW_THREADS = 96;   // >= GF_MAX_J / 2 complex terms
-constexpr int SW_WARPS = SW_THREADS / 32;
-constexpr int CH = 8;
 
 __device__ __forceinline__ double warp_sum(double x)
 {
@@ -29,18 +27,56 @@ __device__ __forceinline__ double warp_sum(double x)
     return x;
 }
 
-template <bool UPPER, bool SOLVE>
-__global__ void __launch_bounds__(SW_THREADS)
-sweep_kernel(int64_t B, const int64_t *__restrict__ n_off, const int64_t *__restrict__ t_off,
-             const int64_t *__restrict__ j_off, const int64_t *__restrict__ w_off,
-             const double *__restrict__ t_all, const double *__restrict__ coef,
-             const double *__restrict__ W_all, const double *Y_all, double *Z_all)
+constexpr int SW2_PROD = 7;                       // producer warps
+constexpr int SW2_THREADS = 32 * (1 + SW2_PROD);
+constexpr int SW2_RS = 16;                        // ring slots (two halves)
+constexpr int SW2_HALF = 8;
+constexpr int SW2_TPL = 3;                        // terms per lane (3 x 32 >= GF_MAX_J / 2)
+constexpr int SW2_JC = 96;
+
+struct Sweep2Smem {
+    double2 dot[SW2_RS][SW2_JC];     // row the state is read through at this step (U_n lower, W_n upper)
+    double2 upd[SW2_RS][SW2_JC];     // row that enters the state after this step (W_n lower, U_n upper)
+    double dec[SW2_RS][SW2_JC];      // decay of the state over the step into this one
+    double yv[SW2_RS];
+    unsigned long long full[2], empty[2];
+};
+
+__device__ __forceinline__ void sw_mbar_init(unsigned long long *mb, int count)
 {
-    __shared__ double s_red[2][SW_WARPS];
-    __shared__ double s_y[2];
-    __shared__ double s_chunk[2][SW_WARPS][CH];     // matmul: the CH sums of a chunk per warp
-    const int tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(mb)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void sw_mbar_inval(unsigned long long *mb)
+{
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(mb)) : "memory");
+}
+__device__ __forceinline__ void sw_mbar_arrive(unsigned long long *mb)
+{
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(mb)) : "memory");
+}
+__device__ __forceinline__ void sw_mbar_wait(unsigned long long *mb, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "SW_MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra.uni SW_MBAR_DONE;\n"
+        "bra.uni SW_MBAR_WAIT;\n"
+        "SW_MBAR_DONE:\n"
+        "}\n" ::"r"((uint32_t)__cvta_generic_to_shared(mb)), "r"(parity) : "memory");
+}
+
+template <bool UPPER, bool SOLVE>
+__global__ void __launch_bounds__(SW2_THREADS)
+sweep2_kernel(int64_t B, const int64_t *__restrict__ n_off, const int64_t *__restrict__ t_off,
+              const int64_t *__restrict__ j_off, const int64_t *__restrict__ w_off,
+              const double *__restrict__ t_all, const double *__restrict__ coef,
+              const double *__restrict__ W_all, const double *Y_all, double *Z_all)
+{
+    extern __shared__ __align__(16) unsigned char sw2_raw[];
+    Sweep2Smem &sm = *reinterpret_cast<Sweep2Smem *>(sw2_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
         const int64_t n0 = n_off[b];
@@ -52,131 +88,106 @@ sweep_kernel(int64_t B, const int64_t *__restrict__ n_off, const int64_t *__rest
         const double *W = W_all + w_off[b];
         const double *Y = Y_all + n0;
         double *Z = Z_all + n0;
-        const bool act = tid < Jc;
-        double ca = 0, cb = 0, cc = 0, cd = 0;
-        if (act) {
-            const double *cf = coef + 4 * (j0 + tid);
-            ca = cf[0]; cb = cf[1]; cc = cf[2]; cd = cf[3];
+        __syncthreads();                           // the ring of the previous sequence is dead
+        if (tid == 0) {
+            if (b != (int64_t)blockIdx.x) {        // not the first sequence of this CTA
+                sw_mbar_inval(&sm.full[0]); sw_mbar_inval(&sm.full[1]);
+                sw_mbar_inval(&sm.empty[0]); sw_mbar_inval(&sm.empty[1]);
+            }
+            sw_mbar_init(&sm.full[0], SW2_HALF); sw_mbar_init(&sm.full[1], SW2_HALF);
+            sw_mbar_init(&sm.empty[0], 1);       sw_mbar_init(&sm.empty[1], 1);
         }
-        double Fc = 0.0, Fs = 0.0;      // this term's two entries of F
-        double prev = 0.0;              // z (solve) or y (matmul) of the neighbouring step
-        double uc_nb = 0.0, us_nb = 0.0, wc_nb = 0.0, ws_nb = 0.0, t_nb = 0.0;  // neighbour row
         __syncthreads();
+        const int64_t n_half = (N + SW2_HALF - 1) / SW2_HALF;       // ring halves to go through
 
-        for (int64_t base = 0; base < N; base += CH) {
-            // rows of this chunk: independent of the chain
-            double tt[CH], uc[CH], us[CH], wc[CH], ws[CH], yy[CH];
+        if (warp == 0) {
+            // ---------------- chain ----------------
+            double Fc[SW2_TPL], Fs[SW2_TPL], gc[SW2_TPL], gs[SW2_TPL];
 #pragma unroll
-            for (int k = 0; k < CH; ++k) {
-                const int64_t m = base + k;
-                const int64_t n = UPPER ? (N - 1 - m) : m;
-                const bool ok = m < N;
-                tt[k] = ok ? t[n] : 0.0;
-                wc[k] = (ok && act) ? W[n * J + tid] : 0.0;
-                ws[k] = (ok && act) ? W[n * J + Jc + tid] : 0.0;
-                yy[k] = (ok && (tid == 0 || !SOLVE)) ? Y[n] : 0.0;    // matmul: every thread needs y
-            }
+            for (int k = 0; k < SW2_TPL; ++k) { Fc[k] = Fs[k] = gc[k] = gs[k] = 0.0; }
+            double prev = 0.0;
+            for (int64_t hr = 0; hr < n_half; ++hr) {
+                const int h = (int)(hr & 1);
+                sw_mbar_wait(&sm.full[h], (uint32_t)((hr >> 1) & 1));
+                const int cnt = (int)((N - hr * SW2_HALF < SW2_HALF) ? (N - hr * SW2_HALF) : SW2_HALF);
+                auto step = [&](const int q) {
+                    const int slot = h * SW2_HALF + q;
+                    const int64_t m = hr * SW2_HALF + q;
+                    double part0 = 0.0, part1 = 0.0;
 #pragma unroll
-            for (int k = 0; k < CH; ++k) {
-                double sn, cs;
-                sincos_cw(cd * tt[k], &sn, &cs);
-                uc[k] = ca * cs + cb * sn;
-                us[k] = ca * sn - cb * cs;
-            }
-            // decay over each step of the chunk (UPPER: t_n - t_{n+1}; lower: t_{n-1} - t_n; both <= 0):
-            // off the chain as well
-            double pk[CH];
-#pragma unroll
-            for (int k = 0; k < CH; ++k) {
-                const double tp = (k == 0) ? t_nb : tt[k - 1];
-                pk[k] = (base + k > 0 && base + k < N) ? exp(cc * (UPPER ? (tt[k] - tp) : (tp - tt[k]))) : 0.0;
-            }
-            if (!SOLVE) {
-                // matmul: the state does not depend on the outputs, so the CH dot products of the
-                // chunk are independent -- one multi-value butterfly and one barrier per chunk
-                double part[CH];
-#pragma unroll
-                for (int k = 0; k < CH; ++k) {
-                    if (base + k > 0) {
-                        const double pr = (k == 0) ? prev : yy[k - 1];
-                        const double a0 = (k == 0) ? (UPPER ? uc_nb : wc_nb) : (UPPER ? uc[k - 1] : wc[k - 1]);
-                        const double a1 = (k == 0) ? (UPPER ? us_nb : ws_nb) : (UPPER ? us[k - 1] : ws[k - 1]);
-                        Fc = pk[k] * fma(a0, pr, Fc);
-                        Fs = pk[k] * fma(a1, pr, Fs);
+                    for (int k = 0; k < SW2_TPL; ++k) {
+                        const int j = lane + 32 * k;
+                        const double p = sm.dec[slot][j];
+                        const double2 d = sm.dot[slot][j];
+                        // F <- p o (F + row_{m-1} prev_{m-1})   (p = 0 at the first step)
+                        Fc[k] = p * fma(gc[k], prev, Fc[k]);
+                        Fs[k] = p * fma(gs[k], prev, Fs[k]);
+                        part0 = fma(d.x, Fc[k], part0);
+                        part1 = fma(d.y, Fs[k], part1);
+                        const double2 u = sm.upd[slot][j];
+                        gc[k] = u.x; gs[k] = u.y;
                     }
-                    part[k] = UPPER ? (wc[k] * Fc + ws[k] * Fs) : (uc[k] * Fc + us[k] * Fs);
+                    const double acc = warp_sum(part0 + part1);
+                    const double yn = sm.yv[slot];
+                    const double zn = SOLVE ? (yn - acc) : (yn + acc);
+                    const int64_t n = UPPER ? (N - 1 - m) : m;
+                    if (lane == 0) Z[n] = zn;
+                    prev = SOLVE ? zn : yn;
+                };
+                if (cnt == SW2_HALF) {
+                    // unrolled: the ring reads of the next steps (and, for the matmul ops, their whole
+                    // butterflies) are scheduled under the reduction of the current one
+#pragma unroll
+                    for (int q = 0; q < SW2_HALF; ++q) step(q);
+                } else {
+                    for (int q = 0; q < cnt; ++q) step(q);
                 }
-                // halving butterfly: after the stages 16, 8, 4 every lane holds one of the CH = 8 sums
-                // (index = lane bits 4..2), then two plain stages
-                {
-                    const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0, h4 = (lane & 4) != 0;
-                    double q4[4], q2[2], q1;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const double send = h16 ? part[i] : part[4 + i], keep = h16 ? part[4 + i] : part[i];
-                        q4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const double send = h8 ? q4[i] : q4[2 + i], keep = h8 ? q4[2 + i] : q4[i];
-                        q2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-                    }
-                    {
-                        const double send = h4 ? q2[0] : q2[1], keep = h4 ? q2[1] : q2[0];
-                        q1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-                    }
-                    q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
-                    q1 += __shfl_xor_sync(0xffffffffu, q1, 1);
-                    // value index held by this lane: bit 2 of k from lane bit 4, bit 1 from bit 3, bit 0 from bit 2
-                    const int kidx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-                    const int par = (int)((base / CH) & 1);
-                    if ((lane & 3) == 0) s_chunk[par][warp][kidx] = q1;
-                    __syncthreads();
-                    if (tid < CH && base + tid < N) {
-                        double acc = 0.0;
-#pragma unroll
-                        for (int w = 0; w < SW_WARPS; ++w) acc += s_chunk[par][w][tid];
-                        const int64_t n = UPPER ? (N - 1 - (base + tid)) : (base + tid);
-                        Z[n] = Y[n] + acc;
-                    }
-                }
-                // carry the neighbour row into the next chunk
-                const int last = (int)((N - base < CH ? N - base : CH) - 1);
-#pragma unroll
-                for (int k = 0; k < CH; ++k)
-                    if (k == last) {
-                        prev = yy[k];
-                        uc_nb = uc[k]; us_nb = us[k]; wc_nb = wc[k]; ws_nb = ws[k]; t_nb = tt[k];
-                    }
-            } else {
-#pragma unroll
-            for (int k = 0; k < CH; ++k) {
-                const int64_t m = base + k;
-                if (m >= N) break;
-                const int64_t n = UPPER ? (N - 1 - m) : m;
-                const int par = (int)(m & 1);
-                if (m > 0) {
-                    const double p = pk[k];
-                    if (UPPER) { Fc = p * (Fc + uc_nb * prev); Fs = p * (Fs + us_nb * prev); }
-                    else       { Fc = p * (Fc + wc_nb * prev); Fs = p * (Fs + ws_nb * prev); }
-                }
-                double part = UPPER ? (wc[k] * Fc + ws[k] * Fs) : (uc[k] * Fc + us[k] * Fs);
-                part = warp_sum(part);
-                if (lane == 0) s_red[par][warp] = part;
-                if (tid == 0) s_y[par] = yy[k];
-                __syncthreads();
-                double acc = 0.0;
-#pragma unroll
-                for (int w = 0; w < SW_WARPS; ++w) acc += s_red[par][w];
-                const double yn = s_y[par];
-                const double zn = yn - acc;
-                if (tid == 0) Z[n] = zn;
-                prev = zn;
-                uc_nb = uc[k]; us_nb = us[k]; wc_nb = wc[k]; ws_nb = ws[k]; t_nb = tt[k];
+                __syncwarp();
+                if (lane == 0) sw_mbar_arrive(&sm.empty[h]);
             }
+        } else {
+            // ---------------- producers: warp w takes the steps m = w - 1 (mod SW2_PROD) ----------------
+            double ca[SW2_TPL], cb[SW2_TPL], cc[SW2_TPL], cd[SW2_TPL];
+#pragma unroll
+            for (int k = 0; k < SW2_TPL; ++k) {
+                const int j = lane + 32 * k;
+                ca[k] = cb[k] = cc[k] = cd[k] = 0.0;
+                if (j < Jc) {
+                    const double *cf = coef + 4 * (j0 + j);
+                    ca[k] = cf[0]; cb[k] = cf[1]; cc[k] = cf[2]; cd[k] = cf[3];
+                }
+            }
+            const int64_t m_end = n_half * SW2_HALF;     // dummy arrivals complete the last half
+            for (int64_t m = warp - 1; m < m_end; m += SW2_PROD) {
+                const int64_t hr = m / SW2_HALF;
+                const int h = (int)(hr & 1);
+                const int slot = (int)(m % SW2_RS);
+                if (hr >= 2) sw_mbar_wait(&sm.empty[h], (uint32_t)(((hr >> 1) - 1) & 1));
+                if (m < N) {
+                    const int64_t n = UPPER ? (N - 1 - m) : m;
+                    const double tn = t[n];
+                    // decay from the previous step of the sweep into this one (<= 0 exponent)
+                    const double dt = (m == 0) ? 0.0 : (UPPER ? (tn - t[n + 1]) : (t[n - 1] - tn));
+#pragma unroll
+                    for (int k = 0; k < SW2_TPL; ++k) {
+                        const int j = lane + 32 * k;
+                        const bool on = j < Jc;
+                        const double wc = on ? W[n * J + j] : 0.0;
+                        const double ws = on ? W[n * J + Jc + j] : 0.0;
+                        double sn, cs;
+                        sincos_cw(cd[k] * tn, &sn, &cs);
+                        const double uc = ca[k] * cs + cb[k] * sn;
+                        const double us = ca[k] * sn - cb[k] * cs;
+                        sm.dot[slot][j] = UPPER ? make_double2(wc, ws) : make_double2(on ? uc : 0.0, on ? us : 0.0);
+                        sm.upd[slot][j] = UPPER ? make_double2(on ? uc : 0.0, on ? us : 0.0) : make_double2(wc, ws);
+                        sm.dec[slot][j] = (m == 0) ? 0.0 : exp(cc[k] * dt);
+                    }
+                    if (lane == 0) sm.yv[slot] = Y[n];
+                }
+                __syncwarp();
+                if (lane == 0) sw_mbar_arrive(&sm.full[h]);
             }
         }
-        __syncthreads();
     }
 }
 
@@ -188,13 +199,27 @@ cudaError_t launch_sweep(int op, int64_t B, const int64_t *n_off, const int64_t 
                          cudaStream_t stream)
 {
     const int grid = (int)(B < 65535 ? B : 65535);
-    switch (op) {
-    case 0: sweep_kernel<false, true><<<grid, SW_THREADS, 0, stream>>>(B, n_off, t_off, j_off, w_off, t, coef, W, Y, Z); break;
-    case 1: sweep_kernel<false, false><<<grid, SW_THREADS, 0, stream>>>(B, n_off, t_off, j_off, w_off, t, coef, W, Y, Z); break;
-    case 2: sweep_kernel<true, true><<<grid, SW_THREADS, 0, stream>>>(B, n_off, t_off, j_off, w_off, t, coef, W, Y, Z); break;
-    default: sweep_kernel<true, false><<<grid, SW_THREADS, 0, stream>>>(B, n_off, t_off, j_off, w_off, t, coef, W, Y, Z); break;
+    {
+        static bool configured = false;
+        if (!configured) {
+            cudaError_t e = cudaSuccess;
+            const int bytes = (int)sizeof(Sweep2Smem);
+            e = cudaFuncSetAttribute(sweep2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(sweep2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(sweep2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(sweep2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+            if (e != cudaSuccess) return e;
+            configured = true;
+        }
+        const size_t smem = sizeof(Sweep2Smem);
+        switch (op) {
+        case 0: sweep2_kernel<false, true><<<grid, SW2_THREADS, smem, stream>>>(B, n_off, t_off, j_off, w_off, t, coef, W, Y, Z); break;
+        case 1: sweep2_kernel<false, false><<<grid, SW2_THREADS, smem, stream>>>(B, n_off, t_off, j_off, w_off, t, coef, W, Y, Z); break;
+        case 2: sweep2_kernel<true, true><<<grid, SW2_THREADS, smem, stream>>>(B, n_off, t_off, j_off, w_off, t, coef, W, Y, Z); break;
+        default: sweep2_kernel<true, false><<<grid, SW2_THREADS, smem, stream>>>(B, n_off, t_off, j_off, w_off, t, coef, W, Y, Z); break;
+        }
+        return cudaGetLastError();
     }
-    return cudaGetLastError();
 }
 
 }  // namespace gf
