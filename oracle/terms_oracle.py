@@ -100,7 +100,7 @@ def get_value_convolved(coeffs, delta, tau):
     cosh = np.cosh(crd)
     norm = 2 * ar / crd ** 2
     K_large = np.sum(norm * (cosh - 1) * np.exp(-cr * tau), axis=-1)
-    crdmt = crd - cr * tau
+    crdmt = np.maximum(crd - cr * tau, 0.0)
     K_small = K_large + np.sum(norm * (crdmt - np.sinh(crdmt)), axis=-1)
     # complex part
     cd = c * dt
@@ -119,7 +119,9 @@ def get_value_convolved(coeffs, delta, tau):
     factor = k0 * norm
     K_large = K_large + np.sum((C1 * cos_term - C2 * sin_term) * factor * cdt, axis=-1)
     K_large = K_large + np.sum((C2 * cos_term + C1 * sin_term) * factor * sdt, axis=-1)
-    dmt = dt - tau
+    # (the overlapping-exposure form is only used for tau < delta: clip, so that exp(c (tau - delta))
+    # cannot overflow where it is discarded anyway)
+    dmt = np.maximum(dt - tau, 0.0)
     dpt = dt + tau
     ec_m, ec_p = np.exp(-c * dmt), np.exp(-c * dpt)
     K_small = K_small + np.sum(2 * (a * c + b * d) * c2pd2 * dmt * norm, axis=-1)
