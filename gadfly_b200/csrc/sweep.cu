@@ -8,7 +8,7 @@
 //
 // One CTA per sequence.  The dependency chain of a sweep is one FMA pair, one dot product and its
 // reduction per step; regenerating the U rows (sincos, exp: ~85 FP64 instructions per term and
-// step) in the same threads would triple the step.  So SW2_PROD producer warps generate the rows
+// step) in the same threads would triple the step.  So SW2_PROD (15) producer warps generate the rows
 // of the coming steps into a shared-memory ring (each warp a step of its own, three terms per
 // lane), and ONE chain warp holds the whole state F (three terms per lane): the dot product is a
 // single warp butterfly -- no cross-warp stage, no __syncthreads on the chain.  Hand-over by
@@ -27,9 +27,16 @@ __device__ __forceinline__ double warp_sum(double x)
     return x;
 }
 
-constexpr int SW2_PROD = 7;                       // producer warps
+#ifndef GF_SW2_PROD
+#define GF_SW2_PROD 15
+#endif
+constexpr int SW2_PROD = GF_SW2_PROD;            // producer warps
 constexpr int SW2_THREADS = 32 * (1 + SW2_PROD);
 constexpr int SW2_RS = 16;                        // ring slots (two halves)
+// A producer warp takes every SW2_PROD-th step.  Its mbarrier waits name a phase by parity only,
+// which is unambiguous as long as the warp never asks for a phase two ahead of the barrier:
+// consecutive steps of a warp must be at most two ring halves apart.
+static_assert(SW2_PROD <= SW2_RS, "producer stride must not exceed the ring");
 constexpr int SW2_HALF = 8;
 constexpr int SW2_TPL = 3;                        // terms per lane (3 x 32 >= GF_MAX_J / 2)
 constexpr int SW2_JC = 96;
