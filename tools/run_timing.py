@@ -1,3 +1,6 @@
+#!/usr/bin/env python
+"""Run one batched log-likelihood (148 solar light curves x 16384 points) so that a library built with
+-DGF_TIMING prints its per-role cycle counts.  usage: GADFLY_B200_LIB=variants/libgadfly_b200_tm.so python tools/run_timing.py"""
 import sys, os
 sys.path.insert(0, os.getcwd())
 import numpy as np, torch

@@ -1,3 +1,6 @@
+#!/usr/bin/env python
+"""Kernel time of the four sweeps (solve / matmul, lower / upper) on a stored factor of one solar light
+curve of 2^18 points, in ms and cycles per step.  usage: python tools/sweep_time.py"""
 import sys, os
 sys.path.insert(0, os.getcwd())
 import numpy as np, torch
