@@ -19,6 +19,9 @@ cudaError_t launch_scan_ref(int mode, const ScanArgs &args, int grid, cudaStream
 cudaError_t launch_scan_fast(int mode, const ScanArgs &args, int jmax, int sm_count,
                              cudaStream_t stream, int *launches);
 bool scan_fast_supports(int mode, int jmax);
+bool scan_small_supports(int mode, int jmax);
+cudaError_t launch_scan_small(int mode, const ScanArgs &args, int jmax, int sm_count,
+                              cudaStream_t stream, int *launches);
 cudaError_t launch_sweep(int op, int64_t B, const int64_t *n_off, const int64_t *t_off,
                          const int64_t *j_off, const int64_t *w_off, const double *t,
                          const double *coef, const double *W, const double *Y, double *Z,
@@ -252,6 +255,11 @@ int run_scan(gf_handle h, int mode, int64_t B, const int64_t *n_off, const int64
             int grid = (int)std::min<int64_t>(B, (int64_t)h->sm_count);
             GF_CUDA(h, gf::launch_scan_ref(mode, A, grid, h->stream));
             h->launches += 1;
+        } else if (!(flags & GF_FLAG_WIDE_KERNEL) && gf::scan_small_supports(mode, g.jmax)) {
+            // every sequence of the batch is narrow (J <= 32): one warp per sequence
+            int n = 0;
+            GF_CUDA(h, gf::launch_scan_small(mode, A, g.jmax, h->sm_count, h->stream, &n));
+            h->launches += n;
         } else {
             int n = 0;
             GF_CUDA(h, gf::launch_scan_fast(mode, A, g.jmax, h->sm_count, h->stream, &n));

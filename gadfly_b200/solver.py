@@ -32,6 +32,7 @@ GF_MAX_J = 176
 FLAG_ASYNC = 1
 FLAG_REFERENCE_ORDER = 2
 FLAG_SHARED_Y = 4
+FLAG_WIDE_KERNEL = 8
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIBNAME = "libgadfly_b200.so"

@@ -57,6 +57,8 @@ enum {
 /* flags */
 #define GF_FLAG_ASYNC 1u          /* do not synchronise before returning */
 #define GF_FLAG_REFERENCE_ORDER 2u /* use the simple reference-order scan kernel (validation) */
+#define GF_FLAG_WIDE_KERNEL 8u     /* do not take the one-warp-per-sequence path for narrow batches
+                                      (all J <= 32); validation of that path against the wide kernel */
 #define GF_FLAG_SHARED_Y 4u        /* y / diag (gf_loglike_batched) are laid out like t: sequence b
                                       reads y[t_off[b] + n], so that one light curve serves many
                                       hyper-parameter sets (stride-0 descriptor of SURVEY.md 8b) */

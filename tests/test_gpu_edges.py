@@ -127,3 +127,72 @@ def test_full_length_light_curve(solver, solar_kernel):
     assert status[0] == 0
     assert logdet[0] == pytest.approx(o_ld, rel=RTOL) and quad[0] == pytest.approx(o_q, rel=RTOL)
     assert quad[0] == pytest.approx(np.sum(nrm * nrm), rel=1e-8)       # |L^-1 L n|^2 = |n|^2
+
+
+def _narrow_kernels():
+    rng = np.random.default_rng(17)
+    def sho(n):
+        return [g.SHOTerm(S0=float(10 ** rng.uniform(0, 3)), w0=float(10 ** rng.uniform(0.5, 3.5)),
+                          Q=float(10 ** rng.uniform(-0.2, 2))) for _ in range(n)]
+    return {2: g.SHOTerm(S0=3.0, w0=40.0, Q=2.5),
+            10: None,                                               # granulation-only, set by the test
+            16: g.StellarOscillatorKernel(terms=sho(8), delta=6e-5),
+            32: g.StellarOscillatorKernel(terms=sho(16), delta=6e-5)}
+
+
+@pytest.mark.parametrize("J", [2, 10, 16, 32])
+def test_narrow_kernels_one_warp_per_sequence(solver, solar_kernel, J):
+    """Batches whose kernels all have J <= 32 take the one-warp-per-sequence kernel
+    (csrc/scan_small.cu): against the oracle, and against the wide kernel on the same inputs."""
+    from gadfly_b200 import solver as S, philox
+    from gadfly_b200.solver import Geometry, KernelBatch
+    k = _narrow_kernels()[J]
+    if k is None:
+        k = g.StellarOscillatorKernel(terms=list(solar_kernel.term.terms[:5]), delta=solar_kernel.delta)
+    assert k.J == J
+    B = 37                                      # more sequences than warps of a CTA, ragged lengths
+    rng = np.random.default_rng(J)
+    lengths = [int(x) for x in rng.integers(1, 200, B)]
+    lengths[0], lengths[1], lengths[2] = 1, 32, 33
+    ts = [np.cumsum(rng.uniform(6.1e-5, 3e-4, n)) for n in lengths]
+    scan = k.scan_coefficients()
+    k0 = np.sum(scan[0]) + np.sum(scan[2]) + scan[6]
+    diags = [np.full(n, 1e-4 * k0) for n in lengths]
+    nrm = [rng.standard_normal(n) for n in lengths]
+    t, dg, nn = map(np.concatenate, (ts, diags, nrm))
+    rows, status = batch.sample([k] * B, t, dg, lengths=lengths, normals=nn, solver=solver, subtract_mean=False)
+    assert status.tolist() == [0] * B
+    xs = []
+    for b in range(B):
+        x_ref = oracle.stream(1, scan, ts[b], nrm[b], diag=diags[b])[0]
+        assert _maxrel(rows[b], x_ref) <= RTOL, b
+        xs.append(x_ref)
+    y = np.concatenate(xs)
+    ll, logdet, quad, status = batch.log_likelihood([k] * B, t, y, dg, lengths=lengths, solver=solver,
+                                                    return_parts=True)
+    ll_w, logdet_w, quad_w, status_w = batch.log_likelihood([k] * B, t, y, dg, lengths=lengths, solver=solver,
+                                                            return_parts=True, flags=S.FLAG_WIDE_KERNEL)
+    assert status.tolist() == [0] * B and status_w.tolist() == [0] * B
+    for b in range(B):
+        o_ld, o_q, _ = oracle.stream(0, scan, ts[b], xs[b], diag=diags[b])
+        assert logdet[b] == pytest.approx(o_ld, rel=RTOL) and quad[b] == pytest.approx(o_q, rel=RTOL), b
+    np.testing.assert_allclose(logdet, logdet_w, rtol=RTOL)
+    np.testing.assert_allclose(quad, quad_w, rtol=RTOL)
+    # fused Philox draws on the narrow path
+    N = 100
+    tt = np.arange(N) * 6e-5
+    dfl = np.full(N, 1e-4 * k0)       # white-noise floor: keeps the smooth single-term cases well conditioned
+    x, st = batch.sample([k] * 3, tt, np.tile(dfl, (3, 1)), seed=9, seq0=4, solver=solver, subtract_mean=False)
+    for b in range(3):
+        assert _maxrel(x[b], oracle.stream(1, scan, tt, philox.normals(9, 4 + b, N), diag=dfl)[0]) <= RTOL
+    # shared light curve, and a sequence that is not positive definite
+    kb = KernelBatch([k] * 4)
+    geom = Geometry.shared_t(4, N)
+    ld1, q1, s1 = solver.loglike(kb, geom, tt, x[0], dfl, flags=S.FLAG_SHARED_Y)
+    o_ld, o_q, _ = oracle.stream(0, scan, tt, x[0], diag=dfl)
+    assert s1.tolist() == [0] * 4 and ld1[3] == pytest.approx(o_ld, rel=RTOL) and q1[3] == pytest.approx(o_q, rel=RTOL)
+    tbad = np.array([0.0, 0.0, 1.0, 2.0])
+    _, _, _, st = batch.log_likelihood([g.SHOTerm(S0=1.0, w0=2.0, Q=3.0)] * 2, np.concatenate([tbad, tbad]),
+                                       np.ones(8), np.concatenate([np.zeros(4), np.ones(4)]), lengths=[4, 4],
+                                       solver=solver, return_parts=True)
+    assert st.tolist() == [2, 0]
