@@ -17,9 +17,10 @@ namespace gf {
 
 namespace {
 
-constexpr int SS_WARPS = 8;
-constexpr int SS_THREADS = 32 * SS_WARPS;
 constexpr int SS_JMAX = 32;
+// CTA shape per tile width: 2 x 8 warps per SM at <= 128 registers for JT <= 16, 1 x 12 warps at
+// <= 168 registers for JT = 32 (the 32-double column does not fit 128 registers without spills)
+template <int JT> struct SmallShape { static constexpr int warps = (JT > 16) ? 12 : 8, ctas = (JT > 16) ? 1 : 2; };
 
 __device__ __forceinline__ double ss_warp_sum(double x)
 {
@@ -29,8 +30,9 @@ __device__ __forceinline__ double ss_warp_sum(double x)
 }
 
 template <int MODE, int JT>
-__global__ void __launch_bounds__(SS_THREADS, 2) scan_small_kernel(ScanArgs A)
+__global__ void __launch_bounds__(32 * SmallShape<JT>::warps, SmallShape<JT>::ctas) scan_small_kernel(ScanArgs A)
 {
+    constexpr int SS_WARPS = SmallShape<JT>::warps;
     __shared__ double2 s_up[SS_WARPS][SS_JMAX];     // (u_i, p_i) of the current row
     __shared__ double s_dw[SS_WARPS][SS_JMAX];      // d_{n-1} w_{n-1,i}
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -147,13 +149,23 @@ __global__ void __launch_bounds__(SS_THREADS, 2) scan_small_kernel(ScanArgs A)
     }
 }
 
-template <int MODE>
-cudaError_t launch_small_mode(const ScanArgs &args, int jmax, int grid, cudaStream_t stream)
+template <int MODE, int JT>
+cudaError_t launch_small_shape(const ScanArgs &args, int sm_count, cudaStream_t stream)
 {
-    if (jmax <= 8)       scan_small_kernel<MODE, 8><<<grid, SS_THREADS, 0, stream>>>(args);
-    else if (jmax <= 16) scan_small_kernel<MODE, 16><<<grid, SS_THREADS, 0, stream>>>(args);
-    else                 scan_small_kernel<MODE, 32><<<grid, SS_THREADS, 0, stream>>>(args);
+    // persistent warps pull sequences from the queue: at most the resident CTAs, at least enough warps
+    constexpr int warps = SmallShape<JT>::warps, ctas = SmallShape<JT>::ctas;
+    const int64_t want = (args.B + warps - 1) / warps;
+    const int grid = (int)(want < (int64_t)ctas * sm_count ? want : (int64_t)ctas * sm_count);
+    scan_small_kernel<MODE, JT><<<grid, 32 * warps, 0, stream>>>(args);
     return cudaGetLastError();
+}
+
+template <int MODE>
+cudaError_t launch_small_mode(const ScanArgs &args, int jmax, int sm_count, cudaStream_t stream)
+{
+    if (jmax <= 8)  return launch_small_shape<MODE, 8>(args, sm_count, stream);
+    if (jmax <= 16) return launch_small_shape<MODE, 16>(args, sm_count, stream);
+    return launch_small_shape<MODE, 32>(args, sm_count, stream);
 }
 
 }  // namespace
@@ -166,12 +178,9 @@ bool scan_small_supports(int mode, int jmax)
 cudaError_t launch_scan_small(int mode, const ScanArgs &args, int jmax, int sm_count,
                               cudaStream_t stream, int *launches)
 {
-    // two CTAs of eight warps per SM, one sequence per warp; persistent warps pull from the queue
-    const int64_t want = (args.B + SS_WARPS - 1) / SS_WARPS;
-    const int grid = (int)(want < 2 * (int64_t)sm_count ? want : 2 * (int64_t)sm_count);
     *launches = 1;
-    if (mode == MODE_LOGLIKE) return launch_small_mode<MODE_LOGLIKE>(args, jmax, grid, stream);
-    return launch_small_mode<MODE_SAMPLE>(args, jmax, grid, stream);
+    if (mode == MODE_LOGLIKE) return launch_small_mode<MODE_LOGLIKE>(args, jmax, sm_count, stream);
+    return launch_small_mode<MODE_SAMPLE>(args, jmax, sm_count, stream);
 }
 
 }  // namespace gf
