@@ -271,7 +271,7 @@ def run_b200(args):
     value = units_per_step / (ms_per_step * 1e-3)
 
     cpu = None
-    if rank == 0 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu:      # reported baseline: rank 0 at N = 1 only
         cpu = cpu_reference(kernel, args.cpu_points, 1, 1)
 
     if rank == 0:
