@@ -99,6 +99,14 @@ class Hyperparameters(list):
                             luminosity=1 * u.L_sun, bandpass=bandpass, name=name, **kwargs)
 
     @classmethod
+    def for_stars(cls, mass, radius, temperature, luminosity, bandpass='SOHO VIRGO', alpha=None):
+        """Arrays of stars at once (extension; gadfly_b200/feeder.py): the same scaling relations
+        over ``[B, 81]`` arrays, returned as a flat :class:`~gadfly_b200.feeder.HyperparameterBatch`
+        (``.star(b)`` gives the reference's list-of-dicts view of one star)."""
+        from .feeder import for_stars
+        return for_stars(mass, radius, temperature, luminosity, bandpass=bandpass, alpha=alpha)
+
+    @classmethod
     def for_star(
             cls, mass, radius, temperature, luminosity,
             bandpass=None, name=None, quiet=False, magnitude=None, alpha=None
