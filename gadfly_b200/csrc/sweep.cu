@@ -165,31 +165,48 @@ sweep2_kernel(int64_t B, const int64_t *__restrict__ n_off, const int64_t *__res
                 }
             }
             const int64_t m_end = n_half * SW2_HALF;     // dummy arrivals complete the last half
+            // inputs of a step are fetched one step of this warp ahead (the W rows come from HBM:
+            // their latency would otherwise sit in front of every step)
+            double tn_n = 0.0, dt_n = 0.0, yv_n = 0.0, wc_n[SW2_TPL], ws_n[SW2_TPL];
+            auto fetch = [&](const int64_t m) {
+                if (m < N) {
+                    const int64_t n = UPPER ? (N - 1 - m) : m;
+                    tn_n = t[n];
+                    dt_n = (m == 0) ? 0.0 : (UPPER ? (tn_n - t[n + 1]) : (t[n - 1] - tn_n));
+                    yv_n = Y[n];
+#pragma unroll
+                    for (int k = 0; k < SW2_TPL; ++k) {
+                        const int j = lane + 32 * k;
+                        wc_n[k] = (j < Jc) ? W[n * J + j] : 0.0;
+                        ws_n[k] = (j < Jc) ? W[n * J + Jc + j] : 0.0;
+                    }
+                }
+            };
+            fetch(warp - 1);
             for (int64_t m = warp - 1; m < m_end; m += SW2_PROD) {
                 const int64_t hr = m / SW2_HALF;
                 const int h = (int)(hr & 1);
                 const int slot = (int)(m % SW2_RS);
+                const double tn = tn_n, dt = dt_n, yv = yv_n;   // decay exponent dt <= 0 (previous step of the sweep)
+                double wc[SW2_TPL], ws[SW2_TPL];
+#pragma unroll
+                for (int k = 0; k < SW2_TPL; ++k) { wc[k] = wc_n[k]; ws[k] = ws_n[k]; }
+                fetch(m + SW2_PROD);
                 if (hr >= 2) sw_mbar_wait(&sm.empty[h], (uint32_t)(((hr >> 1) - 1) & 1));
                 if (m < N) {
-                    const int64_t n = UPPER ? (N - 1 - m) : m;
-                    const double tn = t[n];
-                    // decay from the previous step of the sweep into this one (<= 0 exponent)
-                    const double dt = (m == 0) ? 0.0 : (UPPER ? (tn - t[n + 1]) : (t[n - 1] - tn));
 #pragma unroll
                     for (int k = 0; k < SW2_TPL; ++k) {
                         const int j = lane + 32 * k;
                         const bool on = j < Jc;
-                        const double wc = on ? W[n * J + j] : 0.0;
-                        const double ws = on ? W[n * J + Jc + j] : 0.0;
                         double sn, cs;
                         sincos_cw(cd[k] * tn, &sn, &cs);
                         const double uc = ca[k] * cs + cb[k] * sn;
                         const double us = ca[k] * sn - cb[k] * cs;
-                        sm.dot[slot][j] = UPPER ? make_double2(wc, ws) : make_double2(on ? uc : 0.0, on ? us : 0.0);
-                        sm.upd[slot][j] = UPPER ? make_double2(on ? uc : 0.0, on ? us : 0.0) : make_double2(wc, ws);
+                        sm.dot[slot][j] = UPPER ? make_double2(wc[k], ws[k]) : make_double2(on ? uc : 0.0, on ? us : 0.0);
+                        sm.upd[slot][j] = UPPER ? make_double2(on ? uc : 0.0, on ? us : 0.0) : make_double2(wc[k], ws[k]);
                         sm.dec[slot][j] = (m == 0) ? 0.0 : exp(cc[k] * dt);
                     }
-                    if (lane == 0) sm.yv[slot] = Y[n];
+                    if (lane == 0) sm.yv[slot] = yv;
                 }
                 __syncwarp();
                 if (lane == 0) sw_mbar_arrive(&sm.full[h]);
