@@ -1,4 +1,4 @@
-// K1 / K2 for narrow kernels (J <= 32: up to 16 SHO terms -- granulation-only kernels, single
+// K1 / K2 / K3 for narrow kernels (J <= 32: up to 16 SHO terms -- granulation-only kernels, single
 // terms, the J = 10 option of BASELINE configs[3]): ONE WARP PER SEQUENCE.
 //
 // The big scan (scan_fast.cu) gives a whole SM to one sequence and its step time (~1900 cycles) is
@@ -131,15 +131,20 @@ __global__ void __launch_bounds__(32 * SmallShape<JT>::warps, SmallShape<JT>::ct
                 if (MODE == MODE_SAMPLE) {
                     zn = yn * sqrt(dn);
                     if (lane == q) xl = zn + r2;
-                } else {
+                } else if (MODE == MODE_LOGLIKE) {
                     zn = yn - r2;
                     quad += zn * zn / dn;
+                } else {
+                    // factor: d_n and the row of W (celerite2's blocked column order is this kernel's)
+                    zn = 0.0;
+                    if (lane == q) xl = dn;
+                    if (A.out_W && on) A.out_W[A.w_off[b] + n * (int64_t)J + lane] = wk;
                 }
                 prod *= dn;
                 if ((q & 7) == 7) { logdet += log(prod); prod = 1.0; }
                 dprev = dn; zprev = zn; tprev = tn;
             }
-            if (MODE == MODE_SAMPLE && have) A.out_x[n0 + m] = xl;     // (rows after a failure: unspecified)
+            if (MODE != MODE_LOGLIKE && have) A.out_x[n0 + m] = xl;    // (rows after a failure: unspecified)
         }
         if (lane == 0) {
             if (prod != 1.0) logdet += log(prod);
@@ -173,7 +178,8 @@ cudaError_t launch_small_mode(const ScanArgs &args, int jmax, int sm_count, cuda
 
 bool scan_small_supports(int mode, int jmax)
 {
-    return (mode == MODE_LOGLIKE || mode == MODE_SAMPLE) && jmax <= SS_JMAX;
+    (void)mode;
+    return jmax <= SS_JMAX;
 }
 
 cudaError_t launch_scan_small(int mode, const ScanArgs &args, int jmax, int sm_count,
@@ -181,7 +187,8 @@ cudaError_t launch_scan_small(int mode, const ScanArgs &args, int jmax, int sm_c
 {
     *launches = 1;
     if (mode == MODE_LOGLIKE) return launch_small_mode<MODE_LOGLIKE>(args, jmax, sm_count, stream);
-    return launch_small_mode<MODE_SAMPLE>(args, jmax, sm_count, stream);
+    if (mode == MODE_SAMPLE) return launch_small_mode<MODE_SAMPLE>(args, jmax, sm_count, stream);
+    return launch_small_mode<MODE_FACTOR>(args, jmax, sm_count, stream);
 }
 
 }  // namespace gf

@@ -185,6 +185,17 @@ def test_narrow_kernels_one_warp_per_sequence(solver, solar_kernel, J):
     x, st = batch.sample([k] * 3, tt, np.tile(dfl, (3, 1)), seed=9, seq0=4, solver=solver, subtract_mean=False)
     for b in range(3):
         assert _maxrel(x[b], oracle.stream(1, scan, tt, philox.normals(9, 4 + b, N), diag=dfl)[0]) <= RTOL
+    # stored factor (GaussianProcess.compute) and the sweeps on it, narrow path against the wide one
+    from gadfly_b200.solver import KernelBatch as KB
+    geom1 = Geometry.shared_t(1, N)
+    d_n, W_n, w_off, ld_n, st_n = solver.factor(KB([k]), geom1, tt, dfl)
+    d_w, W_w, _, ld_w, st_w = solver.factor(KB([k]), geom1, tt, dfl, flags=S.FLAG_WIDE_KERNEL)
+    assert st_n[0] == 0 and st_w[0] == 0
+    np.testing.assert_allclose(d_n, d_w, rtol=RTOL)
+    np.testing.assert_allclose(W_n, W_w, rtol=1e-7, atol=1e-9 * np.max(np.abs(W_w)))
+    gp = g.GaussianProcess(k, t=tt, diag=dfl, solver=solver)
+    o_ld, o_q, _ = oracle.stream(0, scan, tt, x[1], diag=dfl)
+    assert gp.log_likelihood(x[1]) == pytest.approx(oracle.log_likelihood_from_stream(o_ld, o_q, N), rel=RTOL)
     # shared light curve, and a sequence that is not positive definite
     kb = KernelBatch([k] * 4)
     geom = Geometry.shared_t(4, N)
