@@ -1,0 +1,94 @@
+#!/usr/bin/env python
+"""Randomised stress of the scan kernels against the CPU oracle: random widths (J = 2 .. 172),
+lengths, cadence patterns (uniform, jittered, gaps, cadence changes), batch sizes and modes.
+Run it under `timeout`: a hang is a finding.  usage: python tools/stress.py [seconds] [seed]"""
+import os
+import sys
+import time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import gadfly_b200 as g
+from gadfly_b200 import batch, solver as S
+from gadfly_b200.solver import Geometry, KernelBatch, default_solver
+import oracle
+
+budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
+seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+rng = np.random.default_rng(seed)
+solver = default_solver()
+sun = g.SolarOscillatorKernel(texp=1 * g.units.min, bandpass='SOHO VIRGO')
+sun_terms = list(sun.term.terms)
+
+
+def random_kernel():
+    kind = rng.integers(0, 3)
+    if kind == 0:       # a slice of the solar kernel
+        n = int(rng.integers(1, 87))
+        start = int(rng.integers(0, 87 - n))
+        return g.StellarOscillatorKernel(terms=sun_terms[start:start + n], delta=sun.delta)
+    n = int(rng.integers(1, 20 if kind == 1 else 87))
+    terms = [g.SHOTerm(S0=float(10 ** rng.uniform(0, 3)), w0=float(10 ** rng.uniform(0.3, 3.8)),
+                       Q=float(10 ** rng.uniform(-0.25, 2.5))) for _ in range(n)]
+    if rng.random() < 0.3:
+        return g.TermSum(*terms) if len(terms) > 1 else terms[0]
+    return g.StellarOscillatorKernel(terms=terms, delta=6e-5)
+
+
+def random_times(n):
+    kind = rng.integers(0, 4)
+    dt = np.full(n, 6e-5 * float(rng.choice([1, 1.44, 30])))
+    if kind == 1:
+        dt *= 1 + 1e-3 * rng.standard_normal(n)
+    elif kind == 2 and n > 4:
+        dt[rng.integers(1, n, size=max(1, n // 50))] += 10 ** rng.uniform(-3, 1.5)
+    elif kind == 3 and n > 20:
+        dt[n // 2:] *= 7.0
+    return float(rng.choice([0.0, 3.0, 2.1e5])) + np.cumsum(np.abs(dt) + 6.05e-5 * (kind == 1))
+
+
+t_end = time.time() + budget
+cases = worst = 0
+while time.time() < t_end:
+    B = int(rng.choice([1, 2, 5, 40, 160]))
+    nk = int(rng.integers(1, 4))
+    kernels = [random_kernel() for _ in range(nk)]
+    ks = [kernels[int(rng.integers(0, nk))] for _ in range(B)]
+    lengths = [int(x) for x in rng.integers(1, int(rng.choice([20, 80, 400])), B)]
+    ts = [random_times(n) for n in lengths]
+    scans = [k.scan_coefficients() for k in ks]
+    k0 = [np.sum(s[0]) + np.sum(s[2]) + s[6] for s in scans]
+    diags = [np.full(n, 1e-4 * abs(a) * 10 ** rng.uniform(0, 2)) for n, a in zip(lengths, k0)]
+    nrm = [rng.standard_normal(n) for n in lengths]
+    t, dg, nn = map(np.concatenate, (ts, diags, nrm))
+    flags = int(rng.choice([0, 0, 0, S.FLAG_WIDE_KERNEL, S.FLAG_REFERENCE_ORDER]))
+    rows, status = batch.sample(ks, t, dg, lengths=lengths, normals=nn, solver=solver, subtract_mean=False,
+                                flags=flags)
+    refs = [oracle.stream(1, scans[b], ts[b], nrm[b], diag=diags[b]) for b in range(B)]
+    ys = []
+    for b in range(B):
+        x_ref, _, st = refs[b]
+        assert (status[b] == 0) == (st == 0), ("status", b, status[b], st, flags)
+        if st == 0:
+            err = np.max(np.abs(rows[b] - x_ref)) / max(np.max(np.abs(x_ref)), 1e-300)
+            worst = max(worst, err)
+            if err > 1e-9:
+                # how well conditioned was it?  smallest pivot over k(0) from the oracle's own factor
+                gp = oracle.OracleGP(scans[b], ts[b], diag=diags[b])
+                dmin = float(np.min(gp.d)) / abs(k0[b]) if hasattr(gp, "d") else float("nan")
+                print(f"  sample dev {err:.1e}  J={ks[b].J} N={lengths[b]} flags={flags} min d/k0={dmin:.1e} "
+                      f"t0={ts[b][0]:.3g} dt0={ts[b][1] - ts[b][0] if lengths[b] > 1 else 0:.3g}", flush=True)
+            assert err <= 1e-5, ("sample", b, err, ks[b].J, lengths[b], flags)
+        ys.append(np.where(np.isfinite(x_ref), x_ref, 0.0) if st == 0 else nrm[b])
+    ll, logdet, quad, status = batch.log_likelihood(ks, t, np.concatenate(ys), dg, lengths=lengths, solver=solver,
+                                                    return_parts=True, flags=flags)
+    for b in range(B):
+        o_ld, o_q, st = oracle.stream(0, scans[b], ts[b], ys[b], diag=diags[b])
+        assert (status[b] == 0) == (st == 0), ("status ll", b, status[b], st, flags)
+        if st == 0:
+            err = max(abs(logdet[b] - o_ld) / max(abs(o_ld), 1e-300), abs(quad[b] - o_q) / max(abs(o_q), 1e-300))
+            worst = max(worst, err)
+            if err > 1e-9:
+                print(f"  loglike dev {err:.1e}  J={ks[b].J} N={lengths[b]} flags={flags}", flush=True)
+            assert err <= 1e-5, ("loglike", b, err, ks[b].J, lengths[b], flags)
+    cases += B
+print(f"stress ok: {cases} sequences, worst relative deviation {worst:.2e}")
