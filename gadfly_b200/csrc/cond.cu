@@ -56,7 +56,7 @@ cond_mean_kernel(const int64_t N, const double *__restrict__ t, const int64_t M,
                     const double tm = t[m], am = alpha[m];
                     if (any) { const double p = exp(-c * (tm - t_last)); s0 *= p; s1 *= p; }
                     double sn, cs;
-                    sincos_cw(d * tm, &sn, &cs);
+                    sincos_cw(__dmul_rn(d, tm), &sn, &cs);
                     s0 = fma(cs, am, s0); s1 = fma(sn, am, s1);
                     t_last = tm; any = true; ++m;
                 }
@@ -64,7 +64,7 @@ cond_mean_kernel(const int64_t N, const double *__restrict__ t, const int64_t M,
                 if (any && on) {
                     const double p = exp(-c * (tq - t_last));
                     double sn, cs;
-                    sincos_cw(d * tq, &sn, &cs);
+                    sincos_cw(__dmul_rn(d, tq), &sn, &cs);
                     contrib = p * ((a * cs + b * sn) * s0 + (a * sn - b * cs) * s1);
                 }
                 const double tot = block_sum(contrib, red);
@@ -78,7 +78,7 @@ cond_mean_kernel(const int64_t N, const double *__restrict__ t, const int64_t M,
                     const double tm = t[m], am = alpha[m];
                     if (any) { const double p = exp(-c * (t_last - tm)); s0 *= p; s1 *= p; }
                     double sn, cs;
-                    sincos_cw(d * tm, &sn, &cs);
+                    sincos_cw(__dmul_rn(d, tm), &sn, &cs);
                     s0 = fma(a * cs + b * sn, am, s0); s1 = fma(a * sn - b * cs, am, s1);
                     t_last = tm; any = true; --m;
                 }
@@ -86,7 +86,7 @@ cond_mean_kernel(const int64_t N, const double *__restrict__ t, const int64_t M,
                 if (any && on) {
                     const double p = exp(-c * (t_last - tq));
                     double sn, cs;
-                    sincos_cw(d * tq, &sn, &cs);
+                    sincos_cw(__dmul_rn(d, tq), &sn, &cs);
                     contrib = p * (cs * s0 + sn * s1);
                 }
                 const double tot = block_sum(contrib, red);

@@ -623,7 +623,7 @@ __device__ __forceinline__ void producer_loop(FastSmem &sm, const ScanArgs &A, c
                                 const int term = lane + 32 * k;
                                 const double2 cdk = sm.Kcd[term];
                                 double sn, cs;
-                                sincos_cw(cdk.y * tau, &sn, &cs);
+                                sincos_cw(__dmul_rn(cdk.y, tau), &sn, &cs);
                                 sm.TabT[i][term] = make_double2(cs, sn);
                                 sm.TabQ[i][term] = make_double2(exp(-cdk.x * tau), exp(cdk.x * tau));
                             }
@@ -633,7 +633,7 @@ __device__ __forceinline__ void producer_loop(FastSmem &sm, const ScanArgs &A, c
                     }
                 }
                 if (tab_ok) {
-                    e_mine = (cur - t_prev) - (double)((lane & 7) + 1) * dtT;
+                    e_mine = __dsub_rn(cur - t_prev, __dmul_rn((double)((lane & 7) + 1), dtT));
                     const bool ok = (lane >= HALF) || (fabs(e_mine) * ps.wmax < 1.0e-8);
                     fast = __all_sync(0xffffffffu, ok);
                     if (!fast) { tab_ok = false; cooldown = 4; }
@@ -691,8 +691,15 @@ __device__ __forceinline__ void producer_loop(FastSmem &sm, const ScanArgs &A, c
                         const double2 Tq = sm.TabQ[ti][term];
                         // phase: angle addition from the base row, first-order correction for the
                         // difference between the rounded phase and the table angle
-                        const double x = cdk.y * ts;
-                        const double eps = (x - xbk) - cdk.y * tau;
+                        // NOT contractible: x must be the ROUNDED product (the reference takes
+                        // cos / sin of fl(d t)), and d * tau the rounded product the table was built
+                        // from.  Left to nvcc these become FMAs on the exact products, the rows are
+                        // then the cosines of un-rounded phases and the difference (up to 0.5 ulp of
+                        // a phase of 1e3..1e4 rad per row) walks away from the reference through the
+                        // base rows: 1e-8 after 2000 steps on a p-mode-only kernel (found by
+                        // tools/stress.py, profiles/r1_v6_stress.txt).
+                        const double x = __dmul_rn(cdk.y, ts);
+                        const double eps = __dsub_rn(__dsub_rn(x, xbk), __dmul_rn(cdk.y, tau));
                         const double c1 = fma(tb.x, T.x, -(tb.y * T.y));
                         const double s1 = fma(tb.y, T.x, tb.x * T.y);
                         const double cs = fma(-eps, s1, c1);
@@ -771,7 +778,7 @@ __device__ __forceinline__ void producer_loop(FastSmem &sm, const ScanArgs &A, c
                             if (rn) { r = qn; qn = 1.0; qi = 1.0; }
                             qk = qn;
                             double sn, cs;
-                            const double x = cdk.y * tm;
+                            const double x = __dmul_rn(cdk.y, tm);   // the rounded phase, as the reference forms it
                             sincos_cw(x, &sn, &cs);
                             sm.PBq[term] = make_double2(qn, qi);
                             sm.PBt[term] = make_double2(cs, sn);

@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(REF_THREADS, 1) scan_ref_kernel(ScanArgs A)
                 double u = 0.0, v = 0.0, p = 1.0;
                 if (colthread) {
                     double sn, cs;
-                    sincos(cd * tn, &sn, &cs);
+                    sincos(__dmul_rn(cd, tn), &sn, &cs);
                     if (tid & 1) { u = ca * sn - cb * cs; v = sn; }
                     else         { u = ca * cs + cb * sn; v = cs; }
                     if (n > 0) {

@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(32 * SmallShape<JT>::warps, SmallShape<JT>::ct
                 double u = 0.0, v = 0.0, p = 1.0;
                 if (on) {
                     double sn, cs;
-                    sincos_cw(cd * tn, &sn, &cs);
+                    sincos_cw(__dmul_rn(cd, tn), &sn, &cs);
                     if (is_sin) { u = ca * sn - cb * cs; v = sn; }
                     else        { u = ca * cs + cb * sn; v = cs; }
                     if (n > 0) {

@@ -199,7 +199,7 @@ sweep2_kernel(int64_t B, const int64_t *__restrict__ n_off, const int64_t *__res
                         const int j = lane + 32 * k;
                         const bool on = j < Jc;
                         double sn, cs;
-                        sincos_cw(cd[k] * tn, &sn, &cs);
+                        sincos_cw(__dmul_rn(cd[k], tn), &sn, &cs);
                         const double uc = ca[k] * cs + cb[k] * sn;
                         const double us = ca[k] * sn - cb[k] * cs;
                         sm.dot[slot][j] = UPPER ? make_double2(wc[k], ws[k]) : make_double2(on ? uc : 0.0, on ? us : 0.0);
