@@ -207,3 +207,24 @@ def test_narrow_kernels_one_warp_per_sequence(solver, solar_kernel, J):
                                        np.ones(8), np.concatenate([np.zeros(4), np.ones(4)]), lengths=[4, 4],
                                        solver=solver, return_parts=True)
     assert st.tolist() == [2, 0]
+
+
+def test_rounded_phase_regressions(solver, solar_kernel):
+    """Two cases the randomised stress tool found (profiles/r1_v6_stress.txt): the rows must be
+    cos / sin of the ROUNDED phase fl(d t) -- an FMA contraction of d * t once made them drift."""
+    # p-mode-only kernel, time stamps accumulated by cumsum (ulp-level irregular): fast producer path
+    pm = g.StellarOscillatorKernel(terms=list(solar_kernel.term.terms[40:84]), delta=solar_kernel.delta)
+    N = 2202
+    t = np.cumsum(np.full(N, 8.64e-5))
+    scan = pm.scan_coefficients()
+    k0 = np.sum(scan[2]) + scan[6]
+    _check(solver, pm, t, diag=5e-3 * k0, seed=3, rtol=1e-11)
+    # JD-like absolute time stamps (phases of 1e9 rad) on narrow random kernels and on the solar kernel
+    rng = np.random.default_rng(23)
+    for nterm in (1, 3, 8):
+        terms = [g.SHOTerm(S0=float(10 ** rng.uniform(0, 3)), w0=float(10 ** rng.uniform(2.5, 3.8)),
+                           Q=float(10 ** rng.uniform(0, 2.5))) for _ in range(nterm)]
+        k = g.StellarOscillatorKernel(terms=terms, delta=6e-5)
+        sc = k.scan_coefficients()
+        _check(solver, k, 2.1e5 + np.cumsum(np.full(300, 6e-5)), diag=1e-3 * (np.sum(sc[2]) + sc[6]), seed=nterm)
+    _check(solver, solar_kernel, 2.1e5 + np.cumsum(np.full(1500, 6e-5)), diag=25.0, seed=9)
