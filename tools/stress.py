@@ -47,7 +47,8 @@ def random_times(n):
 
 
 t_end = time.time() + budget
-cases = worst = dumped = 0
+cases = worst = dumped = api = 0
+worst_api = 0.0
 while time.time() < t_end:
     B = int(rng.choice([1, 2, 5, 40, 160]))
     nmax = int(rng.choice([20, 80, 400, 3000]))
@@ -99,4 +100,32 @@ while time.time() < t_end:
                 print(f"  loglike dev {err:.1e}  J={ks[b].J} N={lengths[b]} flags={flags}", flush=True)
             assert err <= 1e-5, ("loglike", b, err, ks[b].J, lengths[b], flags)
     cases += B
+    # ---- every few batches: the stored-factor API (factor + sweeps) and the fused Philox draws ----
+    if cases % 7 == 0:
+        k = ks[0]
+        n = max(lengths[0], 2)
+        tt = random_times(n)
+        dgn = np.full(n, 1e-3 * abs(k0[0]))
+        ogp = oracle.OracleGP(scans[0], tt, diag=dgn)
+        if np.all(ogp.d > 0):
+            gp = g.GaussianProcess(k, solver=solver)
+            gp.compute(tt, diag=dgn, quiet=True)
+            yv = rng.standard_normal(n) * np.sqrt(abs(k0[0]))
+            checks = {"log_likelihood": (gp.log_likelihood(yv), ogp.log_likelihood(yv)),
+                      "dot_tril": (gp.dot_tril(yv), ogp.dot_tril(yv)),
+                      "apply_inverse": (gp.apply_inverse(yv), ogp.apply_inverse(yv))}
+            for name, (a, b_) in checks.items():
+                a, b_ = np.atleast_1d(a), np.atleast_1d(b_)
+                err = np.max(np.abs(a - b_)) / max(np.max(np.abs(b_)), 1e-300)
+                worst_api = max(worst_api, err)
+                lim = 1e-6 if name == "apply_inverse" else 1e-8       # K^-1 y carries cond(K) eps
+                assert err <= lim, (name, err, k.J, n)
+            from gadfly_b200 import philox
+            xs, st = batch.sample([k], tt, dgn, seed=cases, seq0=3, solver=solver, subtract_mean=False)
+            x_ref = oracle.stream(1, scans[0], tt, philox.normals(cases, 3, n), diag=dgn)[0]
+            err = np.max(np.abs(xs[0] - x_ref)) / max(np.max(np.abs(x_ref)), 1e-300)
+            worst_api = max(worst_api, err)
+            assert err <= 1e-8, ("philox sample", err, k.J, n)
+            api += 1
+print(f"api checks: {api}, worst {worst_api:.2e}")
 print(f"stress ok: {cases} sequences, worst relative deviation {worst:.2e}")
