@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Replay one dumped stress case (tools/stress.py) through the GPU kernels (fast and reference-order)
-and the oracle.  usage: python tools/replay_case.py variants/case88.npz"""
+"""Replay one case dumped by tools/stress.py (gpurun_out/stress_case_*.npz: copy it to variants/ so that
+it travels to the GPU box) through the fast and the reference-order kernels and the oracle, at several
+lengths and on a few re-gridded time axes.  usage: python tools/replay_case.py variants/case.npz"""
 import os
 import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
