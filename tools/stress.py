@@ -126,6 +126,12 @@ while time.time() < t_end:
             err = np.max(np.abs(xs[0] - x_ref)) / max(np.max(np.abs(x_ref)), 1e-300)
             worst_api = max(worst_api, err)
             assert err <= 1e-8, ("philox sample", err, k.J, n)
+            # kernel PSD on a random grid (rtol 1e-12 against the oracle)
+            om = 2 * np.pi * np.sort(10 ** rng.uniform(-1, 4, 257))
+            got = solver.psd(KernelBatch([k]), om)[0]
+            ref = oracle.psd(k.base_coefficients(), om, k.exposure)
+            err = np.max(np.abs(got / ref - 1))
+            assert err <= 1e-12, ("psd", err, k.J)
             api += 1
 print(f"api checks: {api}, worst {worst_api:.2e}")
 print(f"stress ok: {cases} sequences, worst relative deviation {worst:.2e}")
