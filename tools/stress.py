@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Randomised stress of the scan kernels against the CPU oracle: random widths (J = 2 .. 172),
 lengths, cadence patterns (uniform, jittered, gaps, cadence changes), batch sizes and modes.
-Run it under `timeout`: a hang is a finding.  usage: python tools/stress.py [seconds] [seed]"""
+Run it under `timeout`: a hang is a finding.  usage: python tools/stress.py [seconds] [seed] [long_n]"""
 import os
 import sys
 import time
@@ -14,6 +14,7 @@ import oracle
 
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
 seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+long_n = int(sys.argv[3]) if len(sys.argv) > 3 else 0       # > 0: few long sequences of up to this length
 rng = np.random.default_rng(seed)
 solver = default_solver()
 sun = g.SolarOscillatorKernel(texp=1 * g.units.min, bandpass='SOHO VIRGO')
@@ -52,6 +53,8 @@ worst_api = 0.0
 while time.time() < t_end:
     B = int(rng.choice([1, 2, 5, 40, 160]))
     nmax = int(rng.choice([20, 80, 400, 3000]))
+    if long_n:
+        nmax, B = long_n, int(rng.integers(1, 3))
     if nmax > 400:
         B = min(B, 5)                        # the oracle needs ~25 us per step at J = 172
     nk = int(rng.integers(1, 4))
