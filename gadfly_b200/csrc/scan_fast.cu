@@ -1193,13 +1193,17 @@ __global__ void __launch_bounds__(FT_THREADS, 1) scan_fast_kernel(ScanArgs A)
 template <int MODE>
 cudaError_t launch_mode(const ScanArgs &args, int grid, cudaStream_t stream)
 {
-    static bool configured = false;
-    if (!configured) {
+    // the opt-in to > 48 KB of dynamic shared memory is per device (a process may hold handles on
+    // several devices)
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(scan_fast_kernel<MODE>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)sizeof(FastSmem));
         if (e != cudaSuccess) return e;
-        configured = true;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     scan_fast_kernel<MODE><<<grid, FT_THREADS, sizeof(FastSmem), stream>>>(args);
     return cudaGetLastError();

@@ -224,8 +224,10 @@ cudaError_t launch_sweep(int op, int64_t B, const int64_t *n_off, const int64_t 
 {
     const int grid = (int)(B < 65535 ? B : 65535);
     {
-        static bool configured = false;
-        if (!configured) {
+        static bool configured[64] = {};      // per device: a process may hold handles on several
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64 || !configured[dev]) {
             cudaError_t e = cudaSuccess;
             const int bytes = (int)sizeof(Sweep2Smem);
             e = cudaFuncSetAttribute(sweep2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -233,7 +235,7 @@ cudaError_t launch_sweep(int op, int64_t B, const int64_t *n_off, const int64_t 
             if (e == cudaSuccess) e = cudaFuncSetAttribute(sweep2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(sweep2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
             if (e != cudaSuccess) return e;
-            configured = true;
+            if (dev >= 0 && dev < 64) configured[dev] = true;
         }
         const size_t smem = sizeof(Sweep2Smem);
         switch (op) {
