@@ -61,11 +61,20 @@ def solar_kernel():
 
 
 # ---- CPU reference arm --------------------------------------------------------------------
+def host_cores():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_reference(kernel, n_points, steps, warmup):
     """The celerite2-equivalent CPU path on all host cores: one light curve per core,
     loglike + sample per step.  Returns dict(value, cores, sample, ms_per_step)."""
     import oracle
-    cores = oracle.max_threads()
+    # the cores this process may run on -- NOT omp_get_max_threads(): torch.distributed.run exports
+    # OMP_NUM_THREADS=1, which made the round-1 reference arm time one core at N > 1
+    cores = host_cores()
     J = kernel.J
     scan = kernel.scan_coefficients()
     B = cores
@@ -79,8 +88,8 @@ def cpu_reference(kernel, n_points, steps, warmup):
     ddiag = np.full(B, scan[6])
 
     def step():
-        oracle.stream_batch(0, n_off, t_off, j_off, t, y, ddiag, *coef, fast=True)
-        oracle.stream_batch(1, n_off, t_off, j_off, t, y, ddiag, *coef, fast=True)
+        oracle.stream_batch(0, n_off, t_off, j_off, t, y, ddiag, *coef, nthreads=cores, fast=True)
+        oracle.stream_batch(1, n_off, t_off, j_off, t, y, ddiag, *coef, nthreads=cores, fast=True)
 
     for _ in range(warmup):
         step()
@@ -206,6 +215,7 @@ def run_b200(args):
         if world > 1:
             dist.barrier()
 
+    torch.cuda.synchronize()      # the synthetic inputs above were produced on torch's stream
     for i in range(args.warmup):
         step(i)
     sync_all()
@@ -242,16 +252,20 @@ def run_b200(args):
         t_np, y_np, x_np = t_host.numpy(), y_host.numpy(), x_host.numpy()
 
         def e2e_step(i):
+            # the sample call needs only t: issued first and asynchronously, its kernel runs beside
+            # the H2D copy of y (copy-in stream); the log-likelihood kernel then runs beside the D2H
+            # copy of x (copy-out stream).  log_likelihood returns when both results are on the host.
+            solver.sample(kb, geom, t_np, seed=2000 + i, seq0=rank * B, out=x_np, flags=S.FLAG_ASYNC)
             ll = batch.log_likelihood(kb, t_np, y_np, solver=solver)
-            solver.sample(kb, geom, t_np, seed=2000 + i, seq0=rank * B, out=x_np)
             return ll
 
         e2e_step(0)
         sync_all()
         t0 = time.perf_counter()
-        n_e2e = max(1, min(args.steps, 2))
+        n_e2e = max(1, args.steps)
         for i in range(n_e2e):
             ll = e2e_step(1 + i)
+            assert np.all(np.isfinite(ll))
         sync_all()
         dt = time.perf_counter() - t0
         e2e = dict(seconds=dt / n_e2e,
@@ -287,20 +301,25 @@ def run_b200(args):
         except Exception:
             pass
         hbm_achieved = 24.0 * B * N / (dom_ms * 1e-3) / 1e9
-        # DRAM traffic of one launch: bytes per point from the committed ncu capture of the same
-        # kernel (profiles/r1_v6_traffic.json) x the points of this launch
+        # DRAM traffic of one launch of the dominant kernel: only from an ncu capture of THIS launch
+        # geometry (profiles/r2_traffic.json, same B x N), never extrapolated from a smaller one
+        # whose output still fits in L2; otherwise null
         traffic, traffic_src = None, None
         try:
-            with open(os.path.join(ROOT, "profiles", "r1_v6_traffic.json")) as fh:
+            with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as fh:
                 tj = json.load(fh)
-            for name in (f"scan ({dom})", "scan (loglike)"):
-                if name in tj:
-                    per_point = (tj[name]["dram_bytes_read"] + tj[name]["dram_bytes_write"]) / tj["points_per_launch"]
-                    traffic = per_point * B * N
-                    traffic_src = f"{name}: {per_point:.2f} B/point measured by ncu (profiles/r1_v6_traffic.json)"
-                    break
+            ent = tj.get(f"scan ({dom})")
+            if ent and int(ent["points_per_launch"]) == B * N:
+                traffic = float(ent["dram_bytes_read"] + ent["dram_bytes_write"])
+                traffic_src = (f"ncu --set full of scan ({dom}) at {B} x {N} points "
+                               f"(profiles/r2_traffic.json): dram__bytes_read.sum + dram__bytes_write.sum")
         except Exception:
             pass
+        nominal = 148 * 64 * 2 * 1.965e9 / 1e12
+        # executed work: the kernel stores the upper triangle only and spends 3 DFMA per stored
+        # element (8x8 register tiles, 253 of them at J <= 176): 6 flop x 253 x 64 per step
+        nt = ((J + 7) // 8) * ((J + 7) // 8 + 1) // 2
+        executed = 6.0 * 64 * nt * B * N / (dom_ms * 1e-3) / 1e12
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -317,6 +336,11 @@ def run_b200(args):
             "roofline": {
                 "bound": "fp64", "kernel": f"scan ({dom})", "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+                "frac_nominal": achieved / nominal, "peak_nominal": nominal,
+                "executed": {"tflops": executed, "frac": executed / peak if peak else None,
+                             "note": "DFMA actually issued by the matrix warps (3 per stored element of "
+                                     "the upper triangle, padded to 8x8 tiles); `achieved` counts the "
+                                     "algorithmic 4 J^2 of SURVEY 8d"},
                 "peak_source": "DFMA microbenchmark measured in this run (gf_device_info); "
                                "MEASURED_PEAKS.json has no FP64 figure; nominal 148 SM x 64 FMA/clk "
                                "x 2 x 1.965 GHz = 37.2",

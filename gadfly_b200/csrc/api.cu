@@ -41,23 +41,40 @@ enum Slot {
     S_OUT, S_OUTW, S_LOGDET, S_QUAD, S_STATUS, S_OMEGA, S_DELTA, S_W, S_SCRATCH, N_SLOTS
 };
 
+// A staging buffer and the event of its last use (a kernel reading / writing it on the compute
+// stream, or a copy on one of the copy streams).  Every slot is a ping-pong pair: a call takes
+// the buffer whose last use has completed, so that the copies of one call never queue behind the
+// kernel of the previous call (that is what lets H2D(y) run beside the sample kernel and D2H(x)
+// beside the log-likelihood kernel); the second buffer is only allocated when that happens.
 struct Buf {
     void *p = nullptr;
     size_t cap = 0;
+    cudaEvent_t ev = nullptr;
+    bool pending = false;
+    uint64_t stamp = 0;
+};
+struct Pair {
+    Buf b[2];
 };
 
 }  // namespace
 
 struct gf_context {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;       // compute
+    cudaStream_t s_in = nullptr;         // host -> device staging copies
+    cudaStream_t s_out = nullptr;        // device -> host copies of staged outputs
+    cudaEvent_t ev_in = nullptr, ev_k = nullptr, ev_ext = nullptr;
+    bool in_dirty = false;
+    uint64_t stamp = 0;
+    std::vector<Buf *> touched;          // staging buffers the kernel of the current call uses
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int sm_count = 0;
     double fp64_flops = 0.0;
     int64_t launches = 0;
     bool timed = false;
     std::string err;
-    Buf buf[N_SLOTS];
+    Pair buf[N_SLOTS];
 };
 
 namespace {
@@ -65,6 +82,8 @@ namespace {
 struct Guard {
     int prev = -1;
     explicit Guard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); }
+    // entry points that stage buffers: also drop what a failed earlier call may have left behind
+    explicit Guard(gf_handle h) : Guard(h->device) { h->touched.clear(); }
     ~Guard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
@@ -91,33 +110,70 @@ bool is_device_ptr(const void *p)
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
-cudaError_t reserve(gf_handle h, int slot, size_t bytes)
+// A staging buffer of at least `bytes` for `slot` whose previous use is either complete or is
+// ordered before everything `waiter` does from here on.
+cudaError_t acquire(gf_handle h, int slot, size_t bytes, cudaStream_t waiter, Buf **out)
 {
-    Buf &b = h->buf[slot];
-    if (bytes <= b.cap) return cudaSuccess;
-    if (b.p) {
-        cudaError_t e = cudaStreamSynchronize(h->stream);
-        if (e != cudaSuccess) return e;
-        cudaFree(b.p);
-        b.p = nullptr; b.cap = 0;
+    Pair &pr = h->buf[slot];
+    for (Buf &b : pr.b)
+        if (b.pending && cudaEventQuery(b.ev) == cudaSuccess) b.pending = false;
+    cudaGetLastError();   // cudaErrorNotReady of the queries above is not an error
+    Buf *pick = nullptr;
+    for (Buf &b : pr.b)
+        if (!b.pending && b.cap >= bytes) { pick = &b; break; }
+    if (!pick)
+        for (Buf &b : pr.b)
+            if (!b.pending) { pick = &b; break; }
+    if (!pick) pick = (pr.b[0].stamp <= pr.b[1].stamp) ? &pr.b[0] : &pr.b[1];   // the older use
+    if (pick->cap < bytes) {
+        if (pick->pending) {
+            cudaError_t e = cudaEventSynchronize(pick->ev);
+            if (e != cudaSuccess) return e;
+            pick->pending = false;
+        }
+        if (pick->p) { cudaFree(pick->p); pick->p = nullptr; pick->cap = 0; }
+        const size_t cap = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&pick->p, cap);
+        if (e != cudaSuccess) { pick->p = nullptr; return e; }
+        pick->cap = cap;
     }
-    size_t cap = bytes + bytes / 8 + 256;
-    cudaError_t e = cudaMalloc(&b.p, cap);
-    if (e != cudaSuccess) { b.p = nullptr; return e; }
-    b.cap = cap;
+    if (!pick->ev) {
+        cudaError_t e = cudaEventCreateWithFlags(&pick->ev, cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+    }
+    if (pick->pending) {
+        cudaError_t e = cudaStreamWaitEvent(waiter, pick->ev, 0);
+        if (e != cudaSuccess) return e;
+    }
+    *out = pick;
     return cudaSuccess;
 }
 
-// Input that may live on the host: returns a device pointer valid on h->stream.
+// device scratch used by kernels only (never copied): ordered on the compute stream
+cudaError_t reserve(gf_handle h, int slot, size_t bytes, void **p)
+{
+    Buf *b = nullptr;
+    cudaError_t e = acquire(h, slot, bytes, h->stream, &b);
+    if (e != cudaSuccess) return e;
+    h->touched.push_back(b);
+    *p = b->p;
+    return cudaSuccess;
+}
+
+// Input that may live on the host: returns a device pointer valid for the kernel of this call
+// (the copy runs on the copy-in stream; begin_kernel() makes the compute stream wait for it).
 template <typename T>
 cudaError_t stage_in(gf_handle h, int slot, const T *src, size_t count, const T **dev)
 {
     if (!src || count == 0) { *dev = src; return cudaSuccess; }
     if (is_device_ptr(src)) { *dev = src; return cudaSuccess; }
-    cudaError_t e = reserve(h, slot, count * sizeof(T));
+    Buf *b = nullptr;
+    cudaError_t e = acquire(h, slot, count * sizeof(T), h->s_in, &b);
     if (e != cudaSuccess) return e;
-    e = cudaMemcpyAsync(h->buf[slot].p, src, count * sizeof(T), cudaMemcpyHostToDevice, h->stream);
-    *dev = (const T *)h->buf[slot].p;
+    e = cudaMemcpyAsync(b->p, src, count * sizeof(T), cudaMemcpyHostToDevice, h->s_in);
+    h->in_dirty = true;
+    h->touched.push_back(b);
+    *dev = (const T *)b->p;
     return e;
 }
 
@@ -128,26 +184,68 @@ struct Out {
     T *dev = nullptr;
     size_t count = 0;
     bool host = false;
+    Buf *buf = nullptr;
 };
 
 template <typename T>
 cudaError_t stage_out(gf_handle h, int slot, T *dst, size_t count, Out<T> *o)
 {
-    o->user = dst; o->count = count; o->host = false; o->dev = dst;
+    o->user = dst; o->count = count; o->host = false; o->dev = dst; o->buf = nullptr;
     if (!dst || count == 0) return cudaSuccess;
     if (is_device_ptr(dst)) return cudaSuccess;
-    cudaError_t e = reserve(h, slot, count * sizeof(T));
+    cudaError_t e = acquire(h, slot, count * sizeof(T), h->stream, &o->buf);
     if (e != cudaSuccess) return e;
-    o->dev = (T *)h->buf[slot].p;
+    o->dev = (T *)o->buf->p;
     o->host = true;
     return cudaSuccess;
+}
+
+// All inputs of this call are staged: the compute stream waits for the copy-in stream.
+cudaError_t begin_kernel(gf_handle h)
+{
+    if (!h->in_dirty) return cudaSuccess;
+    h->in_dirty = false;
+    cudaError_t e = cudaEventRecord(h->ev_in, h->s_in);
+    if (e != cudaSuccess) return e;
+    return cudaStreamWaitEvent(h->stream, h->ev_in, 0);
+}
+
+// The kernel(s) of this call are launched: stamp the staging buffers they use, and let the
+// copy-out stream wait for them.
+cudaError_t end_kernel(gf_handle h)
+{
+    cudaError_t e = cudaEventRecord(h->ev_k, h->stream);
+    if (e != cudaSuccess) return e;
+    ++h->stamp;
+    for (Buf *b : h->touched) {
+        e = cudaEventRecord(b->ev, h->stream);
+        if (e != cudaSuccess) return e;
+        b->pending = true;
+        b->stamp = h->stamp;
+    }
+    h->touched.clear();
+    return cudaStreamWaitEvent(h->s_out, h->ev_k, 0);
 }
 
 template <typename T>
 cudaError_t finish_out(gf_handle h, const Out<T> &o)
 {
     if (!o.host || !o.user || o.count == 0) return cudaSuccess;
-    return cudaMemcpyAsync(o.user, o.dev, o.count * sizeof(T), cudaMemcpyDeviceToHost, h->stream);
+    cudaError_t e = cudaMemcpyAsync(o.user, o.dev, o.count * sizeof(T), cudaMemcpyDeviceToHost, h->s_out);
+    if (e != cudaSuccess) return e;
+    e = cudaEventRecord(o.buf->ev, h->s_out);
+    o.buf->pending = true;
+    o.buf->stamp = ++h->stamp;
+    return e;
+}
+
+// outputs valid on return (unless GF_FLAG_ASYNC)
+cudaError_t finish_call(gf_handle h, uint32_t flags)
+{
+    if (flags & GF_FLAG_ASYNC) return cudaSuccess;
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(h->s_out);
 }
 
 // Batch geometry shared by the scan entry points.
@@ -205,7 +303,7 @@ int run_scan(gf_handle h, int mode, int64_t B, const int64_t *n_off, const int64
     if (rc != GF_OK) return rc;
     if (B == 0) return GF_OK;
     if (!t || !coef || !ddiag || !status) return fail(h, GF_E_ARG, "null data pointer");
-    Guard guard(h->device);
+    Guard guard(h);
 
     gf::ScanArgs A;
     std::memset(&A, 0, sizeof(A));
@@ -217,9 +315,12 @@ int run_scan(gf_handle h, int mode, int64_t B, const int64_t *n_off, const int64
     const int32_t *order_dev = nullptr;
     GF_CUDA(h, stage_in(h, S_ORDER, (const int32_t *)g.order.data(), (size_t)B, &order_dev));
     A.order = order_dev;
-    GF_CUDA(h, reserve(h, S_COUNTER, sizeof(int)));
-    A.counter = (int *)h->buf[S_COUNTER].p;
-    GF_CUDA(h, cudaMemsetAsync(A.counter, 0, sizeof(int), h->stream));
+    {
+        void *cnt = nullptr;
+        GF_CUDA(h, reserve(h, S_COUNTER, sizeof(int), &cnt));
+        A.counter = (int *)cnt;
+        GF_CUDA(h, cudaMemsetAsync(A.counter, 0, sizeof(int), h->stream));
+    }
     GF_CUDA(h, stage_in(h, S_T, t, (size_t)t_len, &A.t));
     const bool shared_y = (flags & GF_FLAG_SHARED_Y) != 0;
     if (shared_y && mode != gf::MODE_LOGLIKE) return fail(h, GF_E_ARG, "GF_FLAG_SHARED_Y: log-likelihood only");
@@ -242,12 +343,14 @@ int run_scan(gf_handle h, int mode, int64_t B, const int64_t *n_off, const int64
     A.out_x = o_x.dev; A.out_W = o_W.dev; A.quad = o_q.dev; A.status = o_st.dev;
     // the kernels always write logdet: give them scratch when the caller does not want it
     if (!o_ld.dev) {
-        GF_CUDA(h, reserve(h, S_LOGDET, (size_t)B * sizeof(double)));
-        A.logdet = (double *)h->buf[S_LOGDET].p;
+        void *ld = nullptr;
+        GF_CUDA(h, reserve(h, S_LOGDET, (size_t)B * sizeof(double), &ld));
+        A.logdet = (double *)ld;
     } else {
         A.logdet = o_ld.dev;
     }
 
+    GF_CUDA(h, begin_kernel(h));
     {
         Timer timer(h);
         const bool ref = (flags & GF_FLAG_REFERENCE_ORDER) || !gf::scan_fast_supports(mode, g.jmax);
@@ -267,12 +370,14 @@ int run_scan(gf_handle h, int mode, int64_t B, const int64_t *n_off, const int64
         }
     }
 
-    GF_CUDA(h, finish_out(h, o_x));
-    GF_CUDA(h, finish_out(h, o_W));
+    GF_CUDA(h, end_kernel(h));
+    // small outputs first: the caller's scalars do not wait behind the bulk copy
     GF_CUDA(h, finish_out(h, o_ld));
     GF_CUDA(h, finish_out(h, o_q));
     GF_CUDA(h, finish_out(h, o_st));
-    if (!(flags & GF_FLAG_ASYNC)) GF_CUDA(h, cudaStreamSynchronize(h->stream));
+    GF_CUDA(h, finish_out(h, o_x));
+    GF_CUDA(h, finish_out(h, o_W));
+    GF_CUDA(h, finish_call(h, flags));
     return GF_OK;
 }
 
@@ -293,10 +398,15 @@ int gf_create(int device, gf_handle *out)
     h->device = device;
     Guard guard(device);
     e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_k, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_ext, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
-    if (e != cudaSuccess) { delete h; return (int)e; }
+    if (e != cudaSuccess) { gf_destroy(h); return (int)e; }
     *out = h;
     return GF_OK;
 }
@@ -305,11 +415,14 @@ int gf_destroy(gf_handle h)
 {
     if (!h) return GF_OK;
     Guard guard(h->device);
-    cudaStreamSynchronize(h->stream);
-    for (auto &b : h->buf) if (b.p) cudaFree(b.p);
-    cudaEventDestroy(h->ev0);
-    cudaEventDestroy(h->ev1);
-    cudaStreamDestroy(h->stream);
+    for (cudaStream_t st : {h->stream, h->s_in, h->s_out}) if (st) cudaStreamSynchronize(st);
+    for (auto &pr : h->buf)
+        for (auto &b : pr.b) {
+            if (b.p) cudaFree(b.p);
+            if (b.ev) cudaEventDestroy(b.ev);
+        }
+    for (cudaEvent_t ev : {h->ev0, h->ev1, h->ev_in, h->ev_k, h->ev_ext}) if (ev) cudaEventDestroy(ev);
+    for (cudaStream_t st : {h->stream, h->s_in, h->s_out}) if (st) cudaStreamDestroy(st);
     delete h;
     return GF_OK;
 }
@@ -318,7 +431,27 @@ int gf_synchronize(gf_handle h)
 {
     if (!h) return GF_E_ARG;
     Guard guard(h->device);
+    GF_CUDA(h, cudaStreamSynchronize(h->s_in));
     GF_CUDA(h, cudaStreamSynchronize(h->stream));
+    GF_CUDA(h, cudaStreamSynchronize(h->s_out));
+    return GF_OK;
+}
+
+int gf_wait_stream(gf_handle h, void *producer)
+{
+    if (!h) return GF_E_ARG;
+    Guard guard(h->device);
+    GF_CUDA(h, cudaEventRecord(h->ev_ext, (cudaStream_t)producer));
+    GF_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_ext, 0));
+    return GF_OK;
+}
+
+int gf_stream_wait(gf_handle h, void *consumer)
+{
+    if (!h) return GF_E_ARG;
+    Guard guard(h->device);
+    GF_CUDA(h, cudaEventRecord(h->ev_ext, h->stream));
+    GF_CUDA(h, cudaStreamWaitEvent((cudaStream_t)consumer, h->ev_ext, 0));
     return GF_OK;
 }
 
@@ -402,7 +535,7 @@ int gf_sweep_batched(gf_handle h, int op, int64_t B, const int64_t *n_off, const
     if (rc != GF_OK) return rc;
     if (B == 0) return GF_OK;
     if (!t || !coef || !W || !Y || !Z || !w_off) return fail(h, GF_E_ARG, "null data pointer");
-    Guard guard(h->device);
+    Guard guard(h);
     int64_t w_len = 0;
     for (int64_t b = 0; b < B; ++b)
         w_len = std::max(w_len, w_off[b] + (n_off[b + 1] - n_off[b]) * 2 * (j_off[b + 1] - j_off[b]));
@@ -420,6 +553,7 @@ int gf_sweep_batched(gf_handle h, int op, int64_t B, const int64_t *n_off, const
     if (!is_device_ptr(Z)) {
         GF_CUDA(h, stage_out(h, S_OUT, Z, (size_t)g.total_n, &o_z));
         if (!is_device_ptr(Y)) {
+            // (on the compute stream: the buffer was acquired for it)
             GF_CUDA(h, cudaMemcpyAsync(o_z.dev, Y, (size_t)g.total_n * sizeof(double),
                                        cudaMemcpyHostToDevice, h->stream));
             d_Y = o_z.dev;
@@ -430,14 +564,16 @@ int gf_sweep_batched(gf_handle h, int op, int64_t B, const int64_t *n_off, const
         o_z.dev = Z;
         GF_CUDA(h, stage_in(h, S_Y, Y, (size_t)g.total_n, &d_Y));
     }
+    GF_CUDA(h, begin_kernel(h));
     {
         Timer timer(h);
         GF_CUDA(h, gf::launch_sweep(op, B, d_noff, d_toff, d_joff, d_woff, d_t, d_coef, d_W, d_Y,
                                     o_z.dev, h->stream));
         h->launches += 1;
     }
+    GF_CUDA(h, end_kernel(h));
     GF_CUDA(h, finish_out(h, o_z));
-    if (!(flags & GF_FLAG_ASYNC)) GF_CUDA(h, cudaStreamSynchronize(h->stream));
+    GF_CUDA(h, finish_call(h, flags));
     return GF_OK;
 }
 
@@ -451,7 +587,7 @@ int gf_psd_batched(gf_handle h, int64_t B, const int64_t *j_off, const double *c
     if (!j_off || !coef_base || !omega || !out) return fail(h, GF_E_ARG, "null data pointer");
     for (int64_t b = 0; b < B; ++b)
         if (j_off[b + 1] < j_off[b]) return fail(h, GF_E_ARG, "offsets must be non-decreasing");
-    Guard guard(h->device);
+    Guard guard(h);
     const int64_t *d_joff;
     const double *d_coef, *d_delta, *d_omega;
     GF_CUDA(h, stage_in(h, S_JOFF, j_off, (size_t)B + 1, &d_joff));
@@ -460,13 +596,15 @@ int gf_psd_batched(gf_handle h, int64_t B, const int64_t *j_off, const double *c
     GF_CUDA(h, stage_in(h, S_OMEGA, omega, (size_t)F, &d_omega));
     Out<double> o;
     GF_CUDA(h, stage_out(h, S_OUT, out, (size_t)B * (size_t)F, &o));
+    GF_CUDA(h, begin_kernel(h));
     {
         Timer timer(h);
         GF_CUDA(h, gf::launch_psd(B, d_joff, d_coef, d_delta, d_omega, F, o.dev, h->stream));
         h->launches += (B + 65534) / 65535;
     }
+    GF_CUDA(h, end_kernel(h));
     GF_CUDA(h, finish_out(h, o));
-    if (!(flags & GF_FLAG_ASYNC)) GF_CUDA(h, cudaStreamSynchronize(h->stream));
+    GF_CUDA(h, finish_call(h, flags));
     return GF_OK;
 }
 
@@ -480,23 +618,26 @@ int gf_conditional_mean(gf_handle h, int64_t N, const double *t, int64_t M, cons
     if (!ts || !mu || (N > 0 && (!t || !alpha)) || (Jc > 0 && !coef))
         return fail(h, GF_E_ARG, "null data pointer");
     if (Jc > 0x3fffffff) return fail(h, GF_E_ARG, "too many terms");
-    Guard guard(h->device);
+    Guard guard(h);
     const double *d_t, *d_ts, *d_coef, *d_alpha;
     GF_CUDA(h, stage_in(h, S_T, t, (size_t)N, &d_t));
     GF_CUDA(h, stage_in(h, S_OMEGA, ts, (size_t)M, &d_ts));
     GF_CUDA(h, stage_in(h, S_COEF, coef, (size_t)Jc * 4, &d_coef));
     GF_CUDA(h, stage_in(h, S_Y, alpha, (size_t)N, &d_alpha));
-    GF_CUDA(h, reserve(h, S_SCRATCH, (size_t)M * 2 * sizeof(double)));
+    void *scratch = nullptr;
+    GF_CUDA(h, reserve(h, S_SCRATCH, (size_t)M * 2 * sizeof(double), &scratch));
     Out<double> o;
     GF_CUDA(h, stage_out(h, S_OUT, mu, (size_t)M, &o));
+    GF_CUDA(h, begin_kernel(h));
     {
         Timer timer(h);
         GF_CUDA(h, gf::launch_cond_mean(N, d_t, M, d_ts, (int)Jc, d_coef, d_alpha,
-                                        (double *)h->buf[S_SCRATCH].p, o.dev, h->stream));
+                                        (double *)scratch, o.dev, h->stream));
         h->launches += 2;
     }
+    GF_CUDA(h, end_kernel(h));
     GF_CUDA(h, finish_out(h, o));
-    if (!(flags & GF_FLAG_ASYNC)) GF_CUDA(h, cudaStreamSynchronize(h->stream));
+    GF_CUDA(h, finish_call(h, flags));
     return GF_OK;
 }
 

@@ -103,6 +103,24 @@ __device__ __forceinline__ void sincos_cw(double x, double *sn, double *cs)
     *cs = ((q + 1) & 2) ? -c1 : c1;
 }
 
+// log-determinant accumulation without a log per step: a positive normal pivot is split into its
+// mantissa in [1, 2) (multiplied into `prod`, at most 2^8 between flushes) and its binary exponent
+// (summed as an integer), so that no product of pivots can overflow or underflow whatever the
+// flux scale; sum log d = sum log(prod) + ln 2 * esum.  (Subnormal pivots keep their value: their
+// exponent field is 0 and they are multiplied in unscaled.)
+__device__ __forceinline__ void logdet_push(double d, double &prod, int &esum)
+{
+    const int hi = __double2hiint(d);
+    const int ef = (hi >> 20) & 0x7ff;
+    const int e = ef ? ef - 1023 : 0;
+    prod *= __hiloint2double(hi - (e << 20), __double2loint(d));
+    esum += e;
+}
+__device__ __forceinline__ double logdet_total(double logsum, double prod, long long esum)
+{
+    return (logsum + log(prod)) + 0.6931471805599453 * (double)esum;
+}
+
 // Upper-triangular tile enumeration: tile id -> (bi, bj), bi <= bj, row-major over bi.
 __host__ __device__ inline void tile_coords(int tile, int nb, int &bi, int &bj)
 {

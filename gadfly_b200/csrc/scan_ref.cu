@@ -154,7 +154,8 @@ __global__ void __launch_bounds__(REF_THREADS, 1) scan_ref_kernel(ScanArgs A)
             double tmpk = 0.0, r1 = 0.0, r2 = 0.0, uk = 0.0, vk = 0.0;
             if (tid < JP_MAX) {
                 uk = s_u[tid]; vk = s_v[tid];
-                if (n > 0) {
+                // columns beyond nb * TILE were never written by phase 2
+                if (n > 0 && tid < nb * TILE) {
                     for (int s = 0; s < nb; ++s) tmpk += s_part[s][tid];
                 }
                 r1 = tmpk * uk;

@@ -69,6 +69,8 @@ __global__ void __launch_bounds__(32 * SmallShape<JT>::warps, SmallShape<JT>::ct
         for (int i = 0; i < JT; ++i) S[i] = 0.0;
         double wk = 0.0, Fk = 0.0, dprev = 0.0, zprev = 0.0, tprev = 0.0;
         double logdet = 0.0, prod = 1.0, quad = 0.0;
+        int esum8 = 0;
+        long long esum = 0;
         int32_t fail = 0;
 
         for (int64_t base = 0; base < N && fail == 0; base += 32) {
@@ -140,15 +142,14 @@ __global__ void __launch_bounds__(32 * SmallShape<JT>::warps, SmallShape<JT>::ct
                     if (lane == q) xl = dn;
                     if (A.out_W && on) A.out_W[A.w_off[b] + n * (int64_t)J + lane] = wk;
                 }
-                prod *= dn;
-                if ((q & 7) == 7) { logdet += log(prod); prod = 1.0; }
+                logdet_push(dn, prod, esum8);
+                if ((q & 7) == 7) { logdet += log(prod); prod = 1.0; esum += esum8; esum8 = 0; }
                 dprev = dn; zprev = zn; tprev = tn;
             }
             if (MODE != MODE_LOGLIKE && have) A.out_x[n0 + m] = xl;    // (rows after a failure: unspecified)
         }
         if (lane == 0) {
-            if (prod != 1.0) logdet += log(prod);
-            A.logdet[b] = logdet;
+            A.logdet[b] = logdet_total(logdet, prod, esum + esum8);
             if (MODE == MODE_LOGLIKE && A.quad) A.quad[b] = quad;
             A.status[b] = fail;
         }

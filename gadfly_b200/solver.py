@@ -67,6 +67,8 @@ _SIGNATURES = {
     "gf_synchronize": (ctypes.c_int, [ctypes.c_void_p]),
     "gf_last_error": (ctypes.c_char_p, [ctypes.c_void_p]),
     "gf_stream": (ctypes.c_void_p, [ctypes.c_void_p]),
+    "gf_wait_stream": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "gf_stream_wait": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "gf_device_info": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int),
                                       ctypes.POINTER(ctypes.c_double), ctypes.c_int]),
     "gf_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),
@@ -271,6 +273,29 @@ class Solver:
     def synchronize(self):
         self._check(self._lib.gf_synchronize(self._h))
 
+    # Device buffers are touched on the handle's compute stream only (include/gadfly_b200.h,
+    # "Streams"): whatever torch stream produced a CUDA tensor we are handed must be ordered
+    # before our kernels, and torch work that follows an ASYNC call after them.
+    @staticmethod
+    def _cuda_tensors(xs):
+        return [x for x in xs if x is not None and hasattr(x, "data_ptr") and getattr(x, "is_cuda", False)]
+
+    def _order_before(self, *xs):
+        ts = self._cuda_tensors(xs)
+        if ts:
+            import torch
+            cur = torch.cuda.current_stream(ts[0].device).cuda_stream
+            if cur != self.stream:
+                self._check(self._lib.gf_wait_stream(self._h, ctypes.c_void_p(cur)))
+
+    def _order_after(self, flags, *xs):
+        ts = self._cuda_tensors(xs)
+        if ts and (flags & FLAG_ASYNC):
+            import torch
+            cur = torch.cuda.current_stream(ts[0].device).cuda_stream
+            if cur != self.stream:
+                self._check(self._lib.gf_stream_wait(self._h, ctypes.c_void_p(cur)))
+
     @property
     def stream(self):
         return self._lib.gf_stream(self._h)
@@ -306,9 +331,11 @@ class Solver:
         n_off, pn = _i64(geom.n_off)
         t_off, pto = _i64(geom.t_off)
         j_off, pj = _i64(kb.j_off)
+        self._order_before(t, y, diag, logdet, quad, status)
         self._check(self._lib.gf_loglike_batched(
             self._h, B, pn, pto, pj, pt, geom.t_len, py, pd, kb.coef.ctypes.data,
             kb.ddiag.ctypes.data, pl, pq, ps, flags))
+        self._order_after(flags, logdet, quad, status)
         return logdet, quad, status
 
     # -- K2 ----------------------------------------------------------------------------
@@ -328,9 +355,11 @@ class Solver:
         n_off, pn = _i64(geom.n_off)
         t_off, pto = _i64(geom.t_off)
         j_off, pj = _i64(kb.j_off)
+        self._order_before(t, diag, normals, out, logdet, status)
         self._check(self._lib.gf_sample_batched(
             self._h, B, pn, pto, pj, pt, geom.t_len, pd, kb.coef.ctypes.data,
             kb.ddiag.ctypes.data, pn_, int(seed), int(seq0), po, pl, ps, flags))
+        self._order_after(flags, out, logdet, status)
         return out, logdet, status
 
     # -- K3 ----------------------------------------------------------------------------
@@ -362,9 +391,11 @@ class Solver:
         t_off, pto = _i64(geom.t_off)
         j_off, pj = _i64(kb.j_off)
         w_off_arr, pw = _i64(w_off)
+        self._order_before(t, diag, d, W, logdet, status)
         self._check(self._lib.gf_factor_batched(
             self._h, B, pn, pto, pj, pw, pt, geom.t_len, pd, kb.coef.ctypes.data,
             kb.ddiag.ctypes.data, pdd, pW, pl, ps, flags))
+        self._order_after(flags, d, W, logdet, status)
         return d, W, w_off_arr, logdet, status
 
     # -- K4 ----------------------------------------------------------------------------
@@ -382,9 +413,11 @@ class Solver:
         t_off, pto = _i64(geom.t_off)
         j_off, pj = _i64(kb.j_off)
         w_off, pw = _i64(w_off)
+        self._order_before(t, W, Y, Z)
         self._check(self._lib.gf_sweep_batched(
             self._h, int(op), B, pn, pto, pj, pw, pt, geom.t_len, kb.coef.ctypes.data, pW, pY, pZ,
             flags))
+        self._order_after(flags, Z)
         return Z
 
     # -- K5 ----------------------------------------------------------------------------
@@ -397,8 +430,10 @@ class Solver:
         pw, keep = _addr(omega, count=F, name="omega")
         out, po = _out(out, (kb.B, F))
         j_off, pj = _i64(kb.j_off)
+        self._order_before(omega, out)
         self._check(self._lib.gf_psd_batched(
             self._h, kb.B, pj, kb.base.ctypes.data, kb.delta.ctypes.data, pw, F, po, flags))
+        self._order_after(flags, out)
         return out
 
 
@@ -413,8 +448,10 @@ class Solver:
         pts, k2 = _addr(ts, count=M, name="ts")
         pa, k3 = _addr(alpha, count=N, name="alpha")
         out, po = _out(out, (M,))
+        self._order_before(t, ts, alpha, out)
         self._check(self._lib.gf_conditional_mean(
             self._h, N, pt, M, pts, coef.shape[0], coef.ctypes.data, pa, po, flags))
+        self._order_after(flags, out)
         return out
 
 

@@ -27,10 +27,19 @@
  *    gf_last_error() gives a message.  Per-sequence numeric failure (non-positive pivot)
  *    is reported in status[b] = 1 + index of the first d[n] <= 0, 0 if none -- the
  *    condition on which celerite2 raises LinAlgError (reference gadfly/gp.py:188-192).
- *  - No global state except the handle; one CUDA stream per handle; calls on one handle
- *    are serialised by the caller.  Entry points return after the work has completed
- *    (outputs valid), unless GF_FLAG_ASYNC is set, in which case outputs that are device
- *    pointers are valid after gf_synchronize().
+ *  - No global state except the handle; calls on one handle are serialised by the caller.
+ *    Entry points return after the work has completed (outputs valid), unless GF_FLAG_ASYNC
+ *    is set, in which case all outputs are valid after gf_synchronize().
+ *  - Streams.  A handle owns one compute stream (gf_stream) on which every kernel runs, and
+ *    two copy streams for host buffers (staging in, results out), so that the copies of one
+ *    call overlap the kernel of the previous GF_FLAG_ASYNC call (H2D of the next light curves
+ *    beside the running scan, D2H of samples beside the next scan).
+ *    DEVICE pointers are read and written on the compute stream only, and the library does not
+ *    know who produced them: device inputs must be complete with respect to gf_stream(h) when
+ *    the entry point is called, and consumers of device outputs must order themselves after
+ *    it.  gf_wait_stream(h, producer) / gf_stream_wait(h, consumer) insert exactly these
+ *    dependencies (event record + cudaStreamWaitEvent, nothing blocks the host); the Python
+ *    binding calls them for every torch CUDA tensor it is handed.
  */
 #ifndef GADFLY_B200_H
 #define GADFLY_B200_H
@@ -68,8 +77,14 @@ int gf_create(int device, gf_handle *out);
 int gf_destroy(gf_handle h);
 int gf_synchronize(gf_handle h);
 const char *gf_last_error(gf_handle h);
-/* the handle's stream as a cudaStream_t (so callers can record events on it) */
+/* the handle's compute stream as a cudaStream_t (so callers can record events on it) */
 void *gf_stream(gf_handle h);
+/* make the compute stream wait for everything enqueued so far on `producer` (a cudaStream_t;
+ * NULL = the legacy default stream): call it before passing device buffers that `producer` wrote */
+int gf_wait_stream(gf_handle h, void *producer);
+/* make `consumer` (a cudaStream_t) wait for everything enqueued so far on the compute stream:
+ * call it before `consumer` reads device outputs of a GF_FLAG_ASYNC call */
+int gf_stream_wait(gf_handle h, void *consumer);
 /* SM count, measured FP64 FMA peak [flop/s] from a DFMA microbenchmark (0 if !measure) */
 int gf_device_info(gf_handle h, int *sm_count, double *fp64_flops, int measure);
 /* kernels launched by this handle since creation (the bench's gpu_launches claim) */
