@@ -27,6 +27,9 @@ def child(n, reps, dump):
     from gadfly_b200.solver import Geometry, KernelBatch, Solver
     dev = torch.device("cuda", 0)
     kernel = g.SolarOscillatorKernel(texp=1 * g.units.min, bandpass='SOHO VIRGO')
+    if os.environ.get("GADFLY_AB_JC"):     # a narrower kernel: the first Jc terms of the solar one
+        kernel = g.StellarOscillatorKernel(terms=list(kernel.term.terms)[:int(os.environ["GADFLY_AB_JC"])],
+                                           delta=kernel.delta)
     solver = Solver(0)
     info = solver.device_info(measure=True)
     B = info["sm_count"]
@@ -80,7 +83,7 @@ def main():
         dump = f"/tmp/ab_scan_{k}.npz"
         env = dict(os.environ, GADFLY_B200_LIB=os.path.abspath(lib))
         p = subprocess.run([sys.executable, __file__, "--child", str(n), str(reps), dump],
-                           env=env, capture_output=True, text=True, timeout=600)
+                           env=env, capture_output=True, text=True, timeout=150)
         line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]
         if not line:
             print(f"{lib}: FAILED\n{p.stdout[-2000:]}\n{p.stderr[-3000:]}")
