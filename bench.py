@@ -49,6 +49,11 @@ def parse():
                    help="points per light curve of the bounded CPU sample")
     p.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--legs", default="cfg4,cfg5",
+                   help="extra legs after the headline workload (cfg3): BASELINE configs[3] / [4], sharded over "
+                        "the ranks with the NCCL gather inside the timed region; '' for none")
+    p.add_argument("--grid", type=int, default=100000, help="cfg4: hyper-parameter grid points (whole job)")
+    p.add_argument("--psd-stars", type=int, default=10000, help="cfg5: stars (whole job)")
     return p.parse_args()
 
 
@@ -155,6 +160,139 @@ class ClockSampler:
         return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(np.max(mx)),
                     power_w_max=float(np.max(pw)), samples=len(sm), reasons=sorted(reasons))
 
+
+
+# ---- sharded legs: BASELINE configs[3] and [4] ---------------------------------------------
+def _timed(dev, world, fn):
+    """Device time [s] of fn() on torch's current stream, barrier + synchronize on both sides,
+    maximum over ranks."""
+    import torch
+    import torch.distributed as dist
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    v = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        dist.barrier()
+    return float(v.item()), out
+
+
+def leg_cfg4(args, solver, dev, rank, world, peak):
+    """Hyper-parameter grid x one 100 000-point light curve (GF_FLAG_SHARED_Y: passed once), strong
+    scaling: the grid is cut into contiguous blocks (batch.shard_bounds), every rank scans its block,
+    and log L + status of the WHOLE grid are all-gathered by NCCL inside the timed region."""
+    import torch
+    from gadfly_b200 import batch, solver as S, workloads
+    from gadfly_b200.solver import Geometry
+    G, N = args.grid, 100000
+    bounds = batch.shard_bounds(np.ones(G), world)
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    kb, feeder_s = workloads.lattice_batch(G, 3, lo, hi)
+    J = kb.J.astype(np.float64)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(3)                                   # the same light curve on every rank
+    t = torch.arange(N, dtype=torch.float64, device=dev) * 6e-5
+    y = torch.randn(N, dtype=torch.float64, device=dev, generator=gen) * 285.0
+    B = kb.B
+    logdet = torch.empty(B, dtype=torch.float64, device=dev)
+    quad = torch.empty(B, dtype=torch.float64, device=dev)
+    status = torch.empty(B, dtype=torch.int32, device=dev)
+    geom = Geometry.shared_t(B, N)
+
+    def run():
+        solver.loglike(kb, geom, t, y, logdet=logdet, quad=quad, status=status,
+                       flags=S.FLAG_SHARED_Y | S.FLAG_ASYNC)
+        ll = -0.5 * (quad + logdet + N * float(np.log(2 * np.pi)))
+        return batch.gather_concat(ll, bounds), batch.gather_concat(status, bounds)
+
+    # warm-up on a few grid points (allocations, NCCL channels), then ONE timed pass over the grid
+    kw = kb.take(np.arange(min(B, 8)))
+    solver.loglike(kw, Geometry.shared_t(kw.B, N), t, y, flags=S.FLAG_SHARED_Y)
+    if world > 1:
+        batch.gather_concat(torch.zeros(B, dtype=torch.float64, device=dev), bounds)
+    seconds, (ll_all, st_all) = _timed(dev, world, run)
+    assert ll_all.numel() == G and int(st_all.abs().sum().item()) == 0
+    # the gathered vector against a recomputation, on THIS rank's GPU, of a slice that another rank owns
+    other = (rank + 1) % world
+    s_lo = int(bounds[other])
+    s_n = min(8, int(bounds[other + 1]) - s_lo)
+    ks, _ = workloads.lattice_batch(G, 3, s_lo, s_lo + s_n)
+    ll_s = batch.log_likelihood(ks, t, y, solver=solver, flags=S.FLAG_SHARED_Y)
+    got = ll_all[s_lo:s_lo + s_n].cpu().numpy()
+    assert np.array_equal(got, ll_s), (got, ll_s)
+    flops_local = 4.0 * float(np.sum(J * J)) * N
+    return dict(workload=f"BASELINE configs[3]: {G} hyper-parameter sets (solar kernel, S0/w0/Q lattice +-10 %) x "
+                         f"one {N}-point light curve, log-likelihood; grid sharded over {world} rank(s)",
+                grid_points=G, n_points=N, J=int(J.max()), seconds=seconds, scaling="strong",
+                grid_points_per_s=G / seconds, updates_per_s=float(np.mean(J * J)) * G * N / seconds,
+                fp64_frac_per_gpu=flops_local / seconds / peak if peak else None,
+                gather=dict(collective="all_gather_into_tensor (NCCL)" if world > 1 else "none (1 rank)",
+                            in_timed_region=True, bytes_per_rank=int(B * 12), verified=f"{s_n} grid points of rank "
+                            f"{other} recomputed on rank {rank}: bit-identical"),
+                host_feeder_s=feeder_s)
+
+
+def leg_cfg5(args, solver, dev, rank, world, peak):
+    """Kernel PSD of Kepler-like stars on a 10^6-bin grid: stars sharded over the ranks; the rows
+    stay on the rank that made them (10^4 x 10^6 doubles are 80 GB), a per-star checksum (sum over
+    the bins) is all-gathered by NCCL inside the timed region."""
+    import torch
+    from gadfly_b200 import batch, solver as S, workloads
+    n_stars, F, chunk = args.psd_stars, 1000000, 256
+    kb_all, feeder_s = workloads.kepler_like_batch(n_stars, 4)
+    nterm = np.diff(kb_all.j_off).astype(np.float64)
+    bounds = batch.shard_bounds(nterm, world)
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    omega = torch.as_tensor(2 * np.pi * np.linspace(0.01, 8333.0, F), device=dev)
+    out = torch.empty(chunk * F, dtype=torch.float64, device=dev)
+    chunks = [kb_all.take(np.arange(a, min(a + chunk, hi))) for a in range(lo, hi, chunk)]
+    sums = torch.empty(hi - lo, dtype=torch.float64, device=dev)
+
+    def run():
+        pos = 0
+        for kc in chunks:
+            solver.psd(kc, omega, out=out[:kc.B * F], flags=S.FLAG_ASYNC)
+            sums[pos:pos + kc.B] = out[:kc.B * F].view(kc.B, F).sum(dim=1)
+            pos += kc.B
+        return batch.gather_concat(sums, bounds)
+
+    solver.psd(chunks[0], omega, out=out[:chunks[0].B * F])
+    if world > 1:
+        batch.gather_concat(sums, bounds)
+    seconds, all_sums = _timed(dev, world, run)
+    assert all_sums.numel() == n_stars and bool(torch.isfinite(all_sums).all())
+    # one star against the closed form of the reference (gadfly/core.py:33-41) x sinc^2, every bin
+    kc = chunks[-1]
+    solver.psd(kc, omega, out=out[:kc.B * F])
+    row = out[(kc.B - 1) * F:kc.B * F].cpu().numpy()
+    w = omega.cpu().numpy()
+    ref = np.zeros(F)
+    for a, b, c, d in kc.base[kc.j_off[kc.B - 1]:kc.j_off[kc.B]]:
+        w0 = np.sqrt(c * c + d * d)
+        Q = w0 / (2 * c)
+        ref += np.sqrt(2 / np.pi) * (a / (w0 * Q)) * w0 ** 4 / ((w ** 2 - w0 ** 2) ** 2 + (w ** 2 * w0 ** 2 / Q ** 2))
+    arg = 0.5 * kc.delta[kc.B - 1] * w
+    ref *= (np.sin(arg) / arg) ** 2
+    rel = float(np.max(np.abs(row / ref - 1)))
+    assert rel < 1e-11, rel
+    assert abs(float(all_sums[hi - 1].item()) / float(np.sum(row)) - 1) < 1e-12
+    flops_local = 12.0 * float(np.sum(nterm[lo:hi])) * F
+    return dict(workload=f"BASELINE configs[4]: kernel PSD of {n_stars} Kepler-like stars on a {F}-bin grid "
+                         f"(to the Nyquist frequency of the 1-min cadence); stars sharded over {world} rank(s)",
+                stars=n_stars, bins=F, seconds=seconds, scaling="strong",
+                star_bins_per_s=n_stars * float(F) / seconds,
+                fp64_frac_per_gpu=flops_local / seconds / peak if peak else None,
+                hbm_write_GBps_per_gpu=(hi - lo) * F * 8 / seconds / 1e9,
+                gather=dict(collective="all_gather_into_tensor (NCCL)" if world > 1 else "none (1 rank)",
+                            in_timed_region=True, payload="per-star sum over the bins (rows stay sharded)",
+                            bytes_per_rank=int((hi - lo) * 8)),
+                max_rel_vs_closed_form=rel, host_feeder_s=feeder_s)
 
 # ---- the B200 arm -------------------------------------------------------------------------
 def run_b200(args):
@@ -284,6 +422,14 @@ def run_b200(args):
     ms_per_step = ms_total / args.steps
     value = units_per_step / (ms_per_step * 1e-3)
 
+    # free the headline workload's buffers, then the sharded legs (every rank takes part)
+    del y_dev, x_dev
+    torch.cuda.empty_cache()
+    extra = {}
+    for leg in [x for x in args.legs.split(",") if x]:
+        fn = {"cfg4": leg_cfg4, "cfg5": leg_cfg5}[leg]
+        extra[leg] = fn(args, solver, dev, rank, world, info["fp64_flops"])
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:      # reported baseline: rank 0 at N = 1 only
         cpu = cpu_reference(kernel, args.cpu_points, 1, 1)
@@ -360,6 +506,7 @@ def run_b200(args):
                            "api": "gadfly_b200.batch.log_likelihood + Solver.sample on pinned host arrays"}
         if cpu:
             line["cpu_baseline"] = cpu
+        line.update(extra)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

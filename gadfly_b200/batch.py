@@ -113,23 +113,40 @@ def shard(B, rank, world, cost=None):
 
 
 def gather_concat(local, bounds=None, group=None):
-    """All-gather per-unit results (1-D float64/int32 arrays of per-rank length) into the full
-    array on every rank: the only collective of the path.  NCCL for CUDA tensors / when the
-    process group is NCCL, gloo otherwise."""
+    """All-gather per-unit results (1-D arrays of per-rank length) into the full array on every rank:
+    the only collective of the path.  ``local`` is a numpy array or a torch
+    tensor; a CUDA tensor stays on the device and is gathered by NCCL on torch's current stream (the
+    result is a CUDA tensor), anything else goes through the process group's backend and comes back
+    as numpy.  ``bounds`` [world + 1] are the shard boundaries (:func:`shard_bounds`): every rank
+    knows them, so no sizes are exchanged; without them one extra all-gather of the lengths is made."""
     import torch
     import torch.distributed as dist
+    is_tensor = hasattr(local, 'data_ptr')
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return np.asarray(local)
+        return local if is_tensor else np.asarray(local)
     world = dist.get_world_size(group)
     backend = dist.get_backend(group)
-    dev = torch.device('cuda', torch.cuda.current_device()) if backend == 'nccl' else torch.device('cpu')
-    x = torch.as_tensor(np.ascontiguousarray(local)).to(dev)
-    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-    dist.all_gather(sizes, torch.tensor([x.numel()], dtype=torch.int64, device=dev), group=group)
-    sizes = [int(s.item()) for s in sizes]
+    if is_tensor and local.is_cuda:
+        x = local.contiguous()
+    else:
+        dev = torch.device('cuda', torch.cuda.current_device()) if backend == 'nccl' else torch.device('cpu')
+        x = torch.as_tensor(np.ascontiguousarray(local.cpu().numpy() if is_tensor else local)).to(dev)
+    if bounds is not None:
+        sizes = [int(v) for v in np.diff(np.asarray(bounds, dtype=np.int64))]
+        assert len(sizes) == world and sizes[dist.get_rank(group)] == x.numel(), "bounds do not match the shard"
+    else:
+        mine = torch.tensor([x.numel()], dtype=torch.int64, device=x.device)
+        every = torch.empty(world, dtype=torch.int64, device=x.device)
+        dist.all_gather_into_tensor(every, mine, group=group)
+        sizes = every.tolist()
     m = max(sizes) if sizes else 0
-    pad = torch.zeros(m, dtype=x.dtype, device=dev)
-    pad[:x.numel()] = x
-    parts = [torch.empty(m, dtype=x.dtype, device=dev) for _ in range(world)]
-    dist.all_gather(parts, pad, group=group)
-    return torch.cat([p[:s] for p, s in zip(parts, sizes)]).cpu().numpy()
+    if m == 0:
+        out = x.new_empty(0)
+    else:
+        pad = x if x.numel() == m else torch.cat([x, x.new_zeros(m - x.numel())])
+        flat = x.new_empty(world * m)
+        dist.all_gather_into_tensor(flat, pad, group=group)
+        out = flat if all(sz == m for sz in sizes) else torch.cat([flat[r * m:r * m + sz] for r, sz in enumerate(sizes)])
+    if is_tensor and local.is_cuda:
+        return out
+    return out.cpu().numpy()

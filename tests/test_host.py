@@ -160,6 +160,14 @@ full = batch.gather_concat(local)
 status = batch.gather_concat(np.full(hi - lo, rank, dtype=np.int32))
 assert full.tolist() == (np.arange(B) * 1.5).tolist(), full
 assert status.tolist() == [0] * batch.shard(B, 0, 2, cost)[1] + [1] * (B - batch.shard(B, 0, 2, cost)[1])
+# with the shard boundaries known to every rank (no size exchange), and a torch tensor as input
+import torch
+bounds = batch.shard_bounds(cost, 2)
+full2 = batch.gather_concat(torch.as_tensor(local), bounds=bounds)
+assert full2.tolist() == full.tolist()
+# an empty shard on one rank
+e = batch.gather_concat(np.arange(3.0) if rank == 0 else np.empty(0))
+assert e.tolist() == [0.0, 1.0, 2.0]
 dist.barrier(); dist.destroy_process_group()
 print("ok", rank, lo, hi)
 """
@@ -260,3 +268,34 @@ def test_get_value_matches_oracle_and_defining_integral(solar_kernel):
     over = g.SHOTerm(S0=3.0, w0=2.0, Q=0.3)                                          # real terms
     np.testing.assert_allclose(over.get_value(tau), T.get_value(over.base_coefficients(), tau), rtol=1e-13)
     assert solar_kernel.get_value(np.zeros((2, 3))).shape == (2, 3)
+
+
+def test_for_star_matches_independent_evaluation():
+    """(S0, w0, Q) of ``Hyperparameters.for_star`` against tests/golden/for_star.json: the scaling
+    relations of the reference (gadfly/core.py:107-333, scale.py) evaluated independently, scalar by
+    scalar in 40-digit mpmath, from the reference's own data files (tools/make_forstar_fixture.py);
+    the per-star path and the batched feeder."""
+    import json
+    import os
+    import warnings
+    import gadfly_b200 as g
+    from gadfly_b200 import feeder
+    with open(os.path.join(os.path.dirname(__file__), "golden", "for_star.json")) as fh:
+        stars = json.load(fh)["stars"]
+    assert stars["Sun"]["n_terms"] == 86 and stars["KIC 9333184"]["n_terms"] == 62
+    names = list(stars)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        hpb = feeder.for_stars(*[[stars[n][k] for n in names]
+                                 for k in ("mass", "radius", "temperature", "luminosity")])
+        for b, name in enumerate(names):
+            st = stars[name]
+            hp = g.Hyperparameters.for_star(st["mass"], st["radius"], st["temperature"], st["luminosity"],
+                                            bandpass="SOHO VIRGO")
+            assert len(hp) == st["n_terms"]
+            for key in ("S0", "w0", "Q"):
+                got = np.array([p["hyperparameters"][key] for p in hp])
+                np.testing.assert_allclose(got, st[key], rtol=1e-12, err_msg=f"{name} {key}")
+            sl = slice(hpb.j_off[b], hpb.j_off[b + 1])
+            for key, arr in (("S0", hpb.S0), ("w0", hpb.w0), ("Q", hpb.Q)):
+                np.testing.assert_allclose(arr[sl], st[key], rtol=1e-12, err_msg=f"batched {name} {key}")

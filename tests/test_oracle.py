@@ -120,3 +120,32 @@ def test_fast_build_agrees_with_reproducible_build():
                                          [scan[6]] * 2, *[np.tile(scan[i], 2) for i in (2, 3, 4, 5)],
                                          fast=False)
     assert status.tolist() == [0, 0] and out[0, 0] == a[0] and out[1, 1] == a[1]
+
+
+# ---- ground truth from the kernel DEFINITION in extended precision (tools/make_golden_definition.py:
+# (S0, w0, Q) -> dense exposure-integrated covariance by quadrature -> longdouble Cholesky; nothing of
+# oracle/ or gadfly_b200/ is involved in producing it) ------------------------------------------------
+# tolerances: (log-det, log-likelihood, samples and K^-1 y).  Measured deviations of the oracle: logL
+# <= 2e-12, samples <= 5e-10 on the three well-conditioned cases; at the 1-min exposure 2.8e-9 on the
+# samples (the slowest granulation term's a' carries celerite2's own FP64 cancellation).
+DEF_CASES = [("def_solar_200s", 1e-10, 1e-10, 1e-9), ("def_subgiant", 1e-10, 1e-10, 1e-9),
+             ("def_giant", 1e-10, 1e-10, 1e-9), ("def_solar_sc", 1e-9, 1e-10, 2e-8)]
+
+
+@pytest.mark.parametrize("name,tol_ld,tol_ll,tol_x", DEF_CASES)
+def test_oracle_matches_definition_golden(name, tol_ld, tol_ll, tol_x):
+    g = golden(name + ".npz")
+    coeffs = T.sho_sum(list(zip(g["S0"], g["w0"], g["Q"])))
+    scan = T.scan_coefficients(coeffs, float(g["delta"]))
+    # k(0) of the exposure-integrated kernel: sum a' + ddiag  (A.4)
+    assert np.sum(scan[2]) + scan[6] == pytest.approx(float(g["k0"]), rel=10 * tol_ld)
+    gp = oracle.OracleGP(scan, g["t"], diag=g["diag"])
+    assert gp.log_det == pytest.approx(float(g["logdet"]), rel=tol_ld)
+    assert gp.log_likelihood(g["y"]) == pytest.approx(float(g["logl"]), rel=tol_ll)
+    x = gp.dot_tril(g["normals"])
+    assert np.max(np.abs(x - g["x"])) <= tol_x * np.max(np.abs(g["x"]))
+    ai = gp.apply_inverse(g["y"])
+    assert np.max(np.abs(ai - g["alpha"])) <= tol_x * np.max(np.abs(g["alpha"]))
+    # the fused streams
+    logdet, quad, status = oracle.stream(0, scan, g["t"], g["y"], diag=g["diag"])
+    assert status == 0 and quad == pytest.approx(float(g["quad"]), rel=100 * tol_ll)

@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Randomised stress of the scan kernels against the CPU oracle: random widths (J = 2 .. 172),
 lengths, cadence patterns (uniform, jittered, gaps, cadence changes), batch sizes and modes.
-Run it under `timeout`: a hang is a finding.  usage: python tools/stress.py [seconds] [seed] [long_n]"""
+Run it under `timeout`: a hang is a finding.
+usage: python tools/stress.py [seconds] [seed] [long_n] [max_batches]   (max_batches > 0: stop after that many
+batches -- a deterministic case list for tests/test_gpu_baseline.py)"""
 import os
 import sys
 import time
@@ -15,6 +17,7 @@ import oracle
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
 seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 long_n = int(sys.argv[3]) if len(sys.argv) > 3 else 0       # > 0: few long sequences of up to this length
+max_batches = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 rng = np.random.default_rng(seed)
 solver = default_solver()
 sun = g.SolarOscillatorKernel(texp=1 * g.units.min, bandpass='SOHO VIRGO')
@@ -48,9 +51,10 @@ def random_times(n):
 
 
 t_end = time.time() + budget
-cases = worst = dumped = api = 0
+cases = worst = dumped = api = batches = 0
 worst_api = 0.0
-while time.time() < t_end:
+while time.time() < t_end and not (max_batches and batches >= max_batches):
+    batches += 1
     B = int(rng.choice([1, 2, 5, 40, 160]))
     nmax = int(rng.choice([20, 80, 400, 3000]))
     if long_n:
@@ -137,4 +141,4 @@ while time.time() < t_end:
             assert err <= 1e-12, ("psd", err, k.J)
             api += 1
 print(f"api checks: {api}, worst {worst_api:.2e}")
-print(f"stress ok: {cases} sequences, worst relative deviation {worst:.2e}")
+print(f"stress ok: {cases} sequences in {batches} batches, worst relative deviation {worst:.2e}")
