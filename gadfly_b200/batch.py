@@ -65,7 +65,7 @@ def log_likelihood(kernels, t, y, diag=None, lengths=None, mean=0.0, quiet=True,
 
 
 def sample(kernels, t, diag=None, lengths=None, normals=None, seed=0, seq0=0, solver=None,
-           subtract_mean=True, out=None, flags=0):
+           subtract_mean=True, out=None, flags=0, size=None):
     """One GP draw per unit: ``x = L (sqrt(d) o n)``.  ``normals=None`` draws n on the device
     from Philox4x32-10 keyed by ``seed`` and the global unit index ``seq0 + b``
     (reproducible on the host with :mod:`gadfly_b200.philox`).  ``subtract_mean`` applies the
@@ -73,6 +73,21 @@ def sample(kernels, t, diag=None, lengths=None, normals=None, seed=0, seq0=0, so
     kb = _as_batch(kernels)
     geom = _geometry(kb, t, lengths)
     solver = solver or default_solver()
+    if size is not None:
+        # ``size`` realisations per unit on ONE factor (celerite2's sample(size=k), reference
+        # gadfly/gp.py:372-395): returns [B, size, N] (or a list of [size, N_b]), Philox realisation
+        # index seq0 + b size + r
+        k = int(size)
+        x, logdet, status = solver.sample_multi(kb, geom, t, k, diag, normals, seed=seed, seq0=seq0, out=out,
+                                                flags=flags)
+        if hasattr(x, 'data_ptr'):
+            return x, status
+        rows = [x[k * geom.n_off[b]:k * geom.n_off[b + 1]].reshape(k, -1) for b in range(kb.B)]
+        if subtract_mean:
+            for r in rows:
+                if r.size:
+                    r -= r.mean(axis=1, keepdims=True)
+        return (np.stack(rows) if lengths is None else rows), status
     x, logdet, status = solver.sample(kb, geom, t, diag, normals, seed=seed, seq0=seq0, out=out,
                                       flags=flags)
     if hasattr(x, 'data_ptr'):

@@ -29,6 +29,19 @@ cudaError_t launch_sweep(int op, int64_t B, const int64_t *n_off, const int64_t 
 cudaError_t launch_psd(int64_t B, const int64_t *j_off, const double *coef, const double *delta,
                        const double *omega, int64_t F, double *out, cudaStream_t stream);
 cudaError_t measure_fp64_peak(int sm_count, cudaStream_t stream, double *flops);
+cudaError_t launch_multi_prep(int64_t V, int64_t max_n, const int64_t *n_off_v, const int64_t *d_off,
+                              const double *d, const double *normals, uint64_t seed, uint64_t seq0,
+                              double *out, cudaStream_t stream);
+cudaError_t launch_multi_quad(int64_t V, const int64_t *n_off_v, const int64_t *d_off, const double *d,
+                              const double *z, double *quad, cudaStream_t stream);
+struct FftPlan;
+FftPlan *new_fft_plan();
+void delete_fft_plan(FftPlan *fp);
+cudaError_t launch_obs_power(FftPlan *fp, int64_t B, int64_t N, const double *flux, double d, int include_zero,
+                             double2 *spec, double *power, cudaStream_t stream);
+cudaError_t launch_bin_power(int64_t B, int64_t F, int64_t nb, const int64_t *lo, const int64_t *cnt,
+                             const double *x, const double *power, double constant, double *stat,
+                             double *err, cudaStream_t stream);
 cudaError_t launch_cond_mean(int64_t N, const double *t, int64_t M, const double *ts, int Jc,
                              const double *coef, const double *alpha, double *scratch, double *mu,
                              cudaStream_t stream);
@@ -38,7 +51,12 @@ namespace {
 
 enum Slot {
     S_NOFF, S_TOFF, S_JOFF, S_WOFF, S_ORDER, S_COUNTER, S_T, S_Y, S_DIAG, S_COEF, S_DDIAG,
-    S_OUT, S_OUTW, S_LOGDET, S_QUAD, S_STATUS, S_OMEGA, S_DELTA, S_W, S_SCRATCH, N_SLOTS
+    S_OUT, S_OUTW, S_LOGDET, S_QUAD, S_STATUS, S_OMEGA, S_DELTA, S_W, S_SCRATCH,
+    // k right-hand sides on one factor (gf_*_multi): the factor itself and the virtual-sequence descriptors
+    S_MD, S_MW, S_MZ, S_MT, S_MDIAG, S_MCOEF, S_MDDIAG, S_VNOFF, S_VTOFF, S_VJOFF, S_VWOFF, S_VDOFF, S_VCOEF,
+    S_MY, S_MOUT, S_MQUAD,
+    // observed power spectrum
+    S_FLUX, S_SPEC, S_POWER, S_BLO, S_BCNT, S_BAXIS, S_BSTAT, S_BERR, N_SLOTS
 };
 
 // A staging buffer and the event of its last use (a kernel reading / writing it on the compute
@@ -74,6 +92,7 @@ struct gf_context {
     int64_t launches = 0;
     bool timed = false;
     std::string err;
+    gf::FftPlan *fft = nullptr;
     Pair buf[N_SLOTS];
 };
 
@@ -303,7 +322,7 @@ int run_scan(gf_handle h, int mode, int64_t B, const int64_t *n_off, const int64
     if (rc != GF_OK) return rc;
     if (B == 0) return GF_OK;
     if (!t || !coef || !ddiag || !status) return fail(h, GF_E_ARG, "null data pointer");
-    Guard guard(h);
+    Guard guard(h->device);
 
     gf::ScanArgs A;
     std::memset(&A, 0, sizeof(A));
@@ -423,6 +442,7 @@ int gf_destroy(gf_handle h)
         }
     for (cudaEvent_t ev : {h->ev0, h->ev1, h->ev_in, h->ev_k, h->ev_ext}) if (ev) cudaEventDestroy(ev);
     for (cudaStream_t st : {h->stream, h->s_in, h->s_out}) if (st) cudaStreamDestroy(st);
+    if (h->fft) gf::delete_fft_plan(h->fft);
     delete h;
     return GF_OK;
 }
@@ -491,6 +511,7 @@ int gf_loglike_batched(gf_handle h, int64_t B, const int64_t *n_off, const int64
 {
     if (!h) return GF_E_ARG;
     if (B > 0 && (!y || !logdet || !quad)) return fail(h, GF_E_ARG, "null data pointer");
+    h->touched.clear();
     return run_scan(h, gf::MODE_LOGLIKE, B, n_off, t_off, j_off, nullptr, t, t_len, y, diag, coef,
                     ddiag, 0, 0, nullptr, nullptr, 0, logdet, quad, status, flags);
 }
@@ -503,6 +524,7 @@ int gf_sample_batched(gf_handle h, int64_t B, const int64_t *n_off, const int64_
 {
     if (!h) return GF_E_ARG;
     if (B > 0 && !out) return fail(h, GF_E_ARG, "null output pointer");
+    h->touched.clear();
     return run_scan(h, gf::MODE_SAMPLE, B, n_off, t_off, j_off, nullptr, t, t_len, normals, diag,
                     coef, ddiag, seed, seq0, out, nullptr, 0, logdet, nullptr, status, flags);
 }
@@ -515,6 +537,7 @@ int gf_factor_batched(gf_handle h, int64_t B, const int64_t *n_off, const int64_
     if (!h) return GF_E_ARG;
     if (B > 0 && !d) return fail(h, GF_E_ARG, "null output pointer");
     if (W && !w_off) return fail(h, GF_E_ARG, "W needs w_off");
+    h->touched.clear();
     int64_t w_len = 0;
     if (W && B > 0 && n_off && j_off)
         for (int64_t b = 0; b < B; ++b)
@@ -637,6 +660,220 @@ int gf_conditional_mean(gf_handle h, int64_t N, const double *t, int64_t M, cons
     }
     GF_CUDA(h, end_kernel(h));
     GF_CUDA(h, finish_out(h, o));
+    GF_CUDA(h, finish_call(h, flags));
+    return GF_OK;
+}
+
+}  // extern "C"
+
+// ---- k right-hand sides per sequence on one factor ------------------------------------------
+namespace {
+
+// mode 1: samples  out[b][r][:] = L_b (sqrt(d_b) o n_{b,r});   mode 0: quad[b][r] = z^T D^-1 z, z = L_b^-1 y_{b,r}
+int run_multi(gf_handle h, int mode, int64_t B, const int64_t *n_off, const int64_t *t_off,
+              const int64_t *j_off, const double *t, int64_t t_len, const double *diag,
+              const double *coef, const double *ddiag, int64_t k, const double *in /* normals | y */,
+              uint64_t seed, uint64_t seq0, double *out, double *logdet, double *quad, int32_t *status,
+              uint32_t flags)
+{
+    if (!h) return GF_E_ARG;
+    if (k < 1) return fail(h, GF_E_ARG, "k must be >= 1");
+    Geometry g;
+    int rc = check_geometry(h, B, n_off, t_off, j_off, t_len, &g);
+    if (rc != GF_OK) return rc;
+    if (B == 0) return GF_OK;
+    if (!t || !coef || !ddiag || !status) return fail(h, GF_E_ARG, "null data pointer");
+    if (B * k > 0x7fffffff) return fail(h, GF_E_ARG, "too many right-hand sides");
+    Guard guard(h);
+
+    // 1. the inputs the factor and the sweeps share, on the device once
+    const double *d_t, *d_diag, *d_coef, *d_ddiag;
+    GF_CUDA(h, stage_in(h, S_MT, t, (size_t)t_len, &d_t));
+    GF_CUDA(h, stage_in(h, S_MDIAG, diag, (size_t)g.total_n, &d_diag));
+    GF_CUDA(h, stage_in(h, S_MCOEF, coef, (size_t)g.total_j * 4, &d_coef));
+    GF_CUDA(h, stage_in(h, S_MDDIAG, ddiag, (size_t)B, &d_ddiag));
+    // 2. the factor: d[sum N], W[sum N J] in library scratch
+    std::vector<int64_t> w_off((size_t)B);
+    int64_t w_len = 0, max_n = 0;
+    for (int64_t b = 0; b < B; ++b) {
+        w_off[(size_t)b] = w_len;
+        w_len += (n_off[b + 1] - n_off[b]) * 2 * (j_off[b + 1] - j_off[b]);
+        max_n = std::max(max_n, n_off[b + 1] - n_off[b]);
+    }
+    void *d_d = nullptr, *d_W = nullptr;
+    GF_CUDA(h, reserve(h, S_MD, (size_t)std::max<int64_t>(g.total_n, 1) * sizeof(double), &d_d));
+    GF_CUDA(h, reserve(h, S_MW, (size_t)std::max<int64_t>(w_len, 1) * sizeof(double), &d_W));
+    std::vector<Buf *> mine = h->touched;      // run_scan's end_kernel stamps and clears the list
+    rc = run_scan(h, gf::MODE_FACTOR, B, n_off, t_off, j_off, w_off.data(), d_t, t_len, nullptr, d_diag,
+                  d_coef, d_ddiag, 0, 0, (double *)d_d, (double *)d_W, w_len, logdet, nullptr, status,
+                  flags | GF_FLAG_ASYNC);
+    if (rc != GF_OK) return rc;
+    h->touched = mine;
+    // 3. virtual sequences v = b k + r: own samples, shared time stamps, factor and kernel
+    const int64_t V = B * k;
+    std::vector<int64_t> vn((size_t)V + 1), vt((size_t)V), vj((size_t)V + 1), vw((size_t)V), vd((size_t)V);
+    std::vector<double> vcoef;
+    vcoef.reserve((size_t)g.total_j * 4 * (size_t)k);
+    vn[0] = 0; vj[0] = 0;
+    for (int64_t b = 0; b < B; ++b) {
+        const int64_t N = n_off[b + 1] - n_off[b], Jc = j_off[b + 1] - j_off[b];
+        for (int64_t r = 0; r < k; ++r) {
+            const size_t v = (size_t)(b * k + r);
+            vn[v + 1] = vn[v] + N;
+            vj[v + 1] = vj[v] + Jc;
+            vt[v] = t_off[b];
+            vw[v] = w_off[(size_t)b];
+            vd[v] = n_off[b];
+        }
+    }
+    const int64_t *d_vn, *d_vt, *d_vj, *d_vw, *d_vd;
+    const double *d_vcoef = nullptr;
+    GF_CUDA(h, stage_in(h, S_VNOFF, (const int64_t *)vn.data(), (size_t)V + 1, &d_vn));
+    GF_CUDA(h, stage_in(h, S_VTOFF, (const int64_t *)vt.data(), (size_t)V, &d_vt));
+    GF_CUDA(h, stage_in(h, S_VJOFF, (const int64_t *)vj.data(), (size_t)V + 1, &d_vj));
+    GF_CUDA(h, stage_in(h, S_VWOFF, (const int64_t *)vw.data(), (size_t)V, &d_vw));
+    GF_CUDA(h, stage_in(h, S_VDOFF, (const int64_t *)vd.data(), (size_t)V, &d_vd));
+    {
+        // the coefficient rows of sequence b, k times (the sweep kernel reads CSR rows per sequence)
+        void *p = nullptr;
+        GF_CUDA(h, reserve(h, S_VCOEF, (size_t)std::max<int64_t>(g.total_j * k, 1) * 4 * sizeof(double), &p));
+        for (int64_t b = 0; b < B; ++b) {
+            const int64_t Jc = j_off[b + 1] - j_off[b];
+            for (int64_t r = 0; r < k; ++r)
+                GF_CUDA(h, cudaMemcpyAsync((double *)p + 4 * vj[(size_t)(b * k + r)], d_coef + 4 * j_off[b],
+                                           (size_t)Jc * 4 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        }
+        d_vcoef = (const double *)p;
+    }
+    const size_t total_v = (size_t)g.total_n * (size_t)k;
+    const double *d_in = nullptr;
+    GF_CUDA(h, stage_in(h, S_MY, in, total_v, &d_in));
+    if (mode == 1) {
+        Out<double> o;
+        GF_CUDA(h, stage_out(h, S_MOUT, out, total_v, &o));
+        if (o.host) h->touched.push_back(o.buf);
+        GF_CUDA(h, begin_kernel(h));
+        {
+            Timer timer(h);
+            GF_CUDA(h, gf::launch_multi_prep(V, max_n, d_vn, d_vd, (const double *)d_d, d_in, seed, seq0, o.dev, h->stream));
+            GF_CUDA(h, gf::launch_sweep(1, V, d_vn, d_vt, d_vj, d_vw, d_t, d_vcoef, (const double *)d_W, o.dev, o.dev, h->stream));
+            h->launches += 2;
+        }
+        GF_CUDA(h, end_kernel(h));
+        GF_CUDA(h, finish_out(h, o));
+    } else {
+        void *d_z = nullptr;
+        GF_CUDA(h, reserve(h, S_MZ, std::max<size_t>(total_v, 1) * sizeof(double), &d_z));
+        Out<double> oq;
+        GF_CUDA(h, stage_out(h, S_MQUAD, quad, (size_t)V, &oq));
+        if (oq.host) h->touched.push_back(oq.buf);
+        GF_CUDA(h, begin_kernel(h));
+        {
+            Timer timer(h);
+            GF_CUDA(h, gf::launch_sweep(0, V, d_vn, d_vt, d_vj, d_vw, d_t, d_vcoef, (const double *)d_W, d_in, (double *)d_z, h->stream));
+            GF_CUDA(h, gf::launch_multi_quad(V, d_vn, d_vd, (const double *)d_d, (const double *)d_z, oq.dev, h->stream));
+            h->launches += 2;
+        }
+        GF_CUDA(h, end_kernel(h));
+        GF_CUDA(h, finish_out(h, oq));
+    }
+    GF_CUDA(h, finish_call(h, flags));
+    return GF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gf_sample_multi(gf_handle h, int64_t B, const int64_t *n_off, const int64_t *t_off,
+                    const int64_t *j_off, const double *t, int64_t t_len, const double *diag,
+                    const double *coef, const double *ddiag, int64_t k, const double *normals,
+                    uint64_t seed, uint64_t seq0, double *out, double *logdet, int32_t *status,
+                    uint32_t flags)
+{
+    if (!h) return GF_E_ARG;
+    if (B > 0 && !out) return fail(h, GF_E_ARG, "null output pointer");
+    return run_multi(h, 1, B, n_off, t_off, j_off, t, t_len, diag, coef, ddiag, k, normals, seed, seq0,
+                     out, logdet, nullptr, status, flags);
+}
+
+int gf_loglike_multi(gf_handle h, int64_t B, const int64_t *n_off, const int64_t *t_off,
+                     const int64_t *j_off, const double *t, int64_t t_len, const double *diag,
+                     const double *coef, const double *ddiag, int64_t k, const double *y,
+                     double *logdet, double *quad, int32_t *status, uint32_t flags)
+{
+    if (!h) return GF_E_ARG;
+    if (B > 0 && (!y || !quad)) return fail(h, GF_E_ARG, "null data pointer");
+    return run_multi(h, 0, B, n_off, t_off, j_off, t, t_len, diag, coef, ddiag, k, y, 0, 0, nullptr,
+                     logdet, quad, status, flags);
+}
+
+}  // extern "C"
+
+extern "C" {
+
+int gf_power_spectrum_batched(gf_handle h, int64_t B, int64_t N, const double *flux, double d,
+                              int include_zero, double *power, uint32_t flags)
+{
+    if (!h) return GF_E_ARG;
+    if (B < 0 || N < 0) return fail(h, GF_E_ARG, "negative size");
+    if (B == 0 || N == 0) return GF_OK;
+    if (!flux || !power) return fail(h, GF_E_ARG, "null data pointer");
+    if (N > 0x7fffffff || B > 0x7fffffff) return fail(h, GF_E_ARG, "too large for one cuFFT plan");
+    Guard guard(h);
+    if (!h->fft) h->fft = gf::new_fft_plan();
+    const int64_t NC = N / 2 + 1, nout = NC - (include_zero ? 0 : 1);
+    const double *d_flux;
+    GF_CUDA(h, stage_in(h, S_FLUX, flux, (size_t)(B * N), &d_flux));
+    void *spec = nullptr;
+    GF_CUDA(h, reserve(h, S_SPEC, (size_t)(B * NC) * sizeof(double2), &spec));
+    Out<double> o;
+    GF_CUDA(h, stage_out(h, S_POWER, power, (size_t)(B * nout), &o));
+    if (o.host) h->touched.push_back(o.buf);
+    GF_CUDA(h, begin_kernel(h));
+    {
+        Timer timer(h);
+        GF_CUDA(h, gf::launch_obs_power(h->fft, B, N, d_flux, d, include_zero, (double2 *)spec, o.dev, h->stream));
+        h->launches += 1;      // our normalisation kernel (the transform is cuFFT's)
+    }
+    GF_CUDA(h, end_kernel(h));
+    GF_CUDA(h, finish_out(h, o));
+    GF_CUDA(h, finish_call(h, flags));
+    return GF_OK;
+}
+
+int gf_bin_power_batched(gf_handle h, int64_t B, int64_t F, int64_t nb, const int64_t *lo,
+                         const int64_t *cnt, const double *axis, const double *power, double constant,
+                         double *stat, double *err, uint32_t flags)
+{
+    if (!h) return GF_E_ARG;
+    if (B < 0 || F < 0 || nb < 0) return fail(h, GF_E_ARG, "negative size");
+    if (B == 0 || nb == 0) return GF_OK;
+    if (!lo || !cnt || !axis || !power || !stat || !err) return fail(h, GF_E_ARG, "null data pointer");
+    for (int64_t k = 0; k < nb; ++k)
+        if (lo[k] < 0 || cnt[k] < 0 || lo[k] + cnt[k] > F) return fail(h, GF_E_ARG, "bin range outside the axis");
+    if (!(constant > 0.0)) return fail(h, GF_E_ARG, "constant must be positive");
+    Guard guard(h);
+    const int64_t *d_lo, *d_cnt;
+    const double *d_axis, *d_power;
+    GF_CUDA(h, stage_in(h, S_BLO, lo, (size_t)nb, &d_lo));
+    GF_CUDA(h, stage_in(h, S_BCNT, cnt, (size_t)nb, &d_cnt));
+    GF_CUDA(h, stage_in(h, S_BAXIS, axis, (size_t)F, &d_axis));
+    GF_CUDA(h, stage_in(h, S_POWER, power, (size_t)(B * F), &d_power));
+    Out<double> os, oe;
+    GF_CUDA(h, stage_out(h, S_BSTAT, stat, (size_t)(B * nb), &os));
+    GF_CUDA(h, stage_out(h, S_BERR, err, (size_t)(B * nb), &oe));
+    if (os.host) h->touched.push_back(os.buf);
+    if (oe.host) h->touched.push_back(oe.buf);
+    GF_CUDA(h, begin_kernel(h));
+    {
+        Timer timer(h);
+        GF_CUDA(h, gf::launch_bin_power(B, F, nb, d_lo, d_cnt, d_axis, d_power, constant, os.dev, oe.dev, h->stream));
+        h->launches += 1;
+    }
+    GF_CUDA(h, end_kernel(h));
+    GF_CUDA(h, finish_out(h, os));
+    GF_CUDA(h, finish_out(h, oe));
     GF_CUDA(h, finish_call(h, flags));
     return GF_OK;
 }

@@ -15,7 +15,8 @@ import numpy as np
 from . import units as u
 from .units import to_value
 
-__all__ = ['PowerSpectrum', 'kernel_psd', 'bin_power_spectrum', 'plot_power_spectrum']
+__all__ = ['PowerSpectrum', 'kernel_psd', 'bin_power_spectrum', 'plot_power_spectrum',
+           'power_spectra', 'bin_power_spectra', 'bin_ranges']
 
 
 def kernel_psd(kernels, frequency, solver=None, out=None):
@@ -33,6 +34,65 @@ def kernel_psd(kernels, frequency, solver=None, out=None):
     if hasattr(res, 'data_ptr'):
         return res
     return res[0].reshape(freq.shape) if single else res.reshape((len(klist),) + freq.shape)
+
+
+# ---- the same estimators for B light curves at once, on the device -------------
+def power_spectra(flux, d_days, include_zero_freq=False, solver=None, out=None):
+    """FFT power spectra of B evenly sampled light curves ``flux[B, N]`` [ppm] (numpy array or CUDA
+    tensor: a tensor never leaves the device) with the reference's normalisation
+    (``PowerSpectrum._fft``, gadfly/psd.py:566-587).  -> (frequency[F] uHz, power[B, F] ppm^2/uHz, norm)."""
+    from .solver import default_solver
+    solver = solver or default_solver()
+    if hasattr(flux, 'data_ptr'):
+        B, N = (1, flux.numel()) if flux.dim() == 1 else (flux.shape[0], flux.shape[1])
+    else:
+        flux = np.ascontiguousarray(np.atleast_2d(flux), dtype=np.float64)
+        B, N = flux.shape
+    d = d_days * 86400.0 * 1e-6
+    freq = np.fft.rfftfreq(N, d)
+    if not include_zero_freq:
+        freq = freq[1:]
+    if out is None and hasattr(flux, 'data_ptr') and flux.is_cuda:
+        import torch
+        out = torch.empty((B, len(freq)), dtype=torch.float64, device=flux.device)
+    power = solver.power_spectrum(flux, B, N, d, include_zero=include_zero_freq, out=out)
+    return freq, power, d / (2 * np.pi) ** 0.5 / N
+
+
+def bin_ranges(axis, bins):
+    """Index ranges of ``scipy.stats.binned_statistic``'s bins on a monotone axis (the last bin is
+    closed on the right): -> (edges[nb + 1], lo[nb], cnt[nb])."""
+    axis = np.asarray(axis, dtype=float)
+    edges = np.linspace(axis.min(), axis.max(), int(bins) + 1) if np.isscalar(bins) else np.asarray(bins, dtype=float)
+    nb = len(edges) - 1
+    lo = np.searchsorted(axis, edges[:-1], side='left')
+    hi = np.searchsorted(axis, edges[1:], side='left')
+    hi[-1] = np.searchsorted(axis, edges[-1], side='right')
+    return edges, lo.astype(np.int64), (hi - lo).astype(np.int64)
+
+
+def bin_power_spectra(frequency, power, bins=None, log=True, constant=1, solver=None):
+    """``bin_power_spectrum`` (reference gadfly/psd.py:229-297) for B spectra ``power[B, F]`` on one
+    frequency grid, on the device.  -> (bin centre frequencies[nb], stat[B, nb], err[B, nb])."""
+    from .solver import default_solver
+    solver = solver or default_solver()
+    freq = np.asarray(frequency, dtype=float)
+    axis = np.log10(freq) if log else freq
+    if bins is None:
+        bins = max(len(axis) // 10000, 1)
+    edges, lo, cnt = bin_ranges(axis, bins)
+    B = 1 if (hasattr(power, 'dim') and power.dim() == 1) or np.ndim(power) == 1 else power.shape[0]
+    stat = err = None
+    if hasattr(power, 'data_ptr') and power.is_cuda:
+        import torch
+        stat = torch.empty((B, len(lo)), dtype=torch.float64, device=power.device)
+        err = torch.empty((B, len(lo)), dtype=torch.float64, device=power.device)
+        axis_in = torch.as_tensor(axis, device=power.device)
+    else:
+        axis_in = axis
+    stat, err = solver.bin_power(power, B, axis_in, lo, cnt, constant=constant, stat=stat, err=err)
+    centers = 0.5 * (edges[1:] + edges[:-1])
+    return (10 ** centers if log else centers), stat, err
 
 
 def _spectral_binning(y, all_x, lo, hi):

@@ -79,6 +79,12 @@ _SIGNATURES = {
     "gf_sample_batched": (ctypes.c_int, [
         ctypes.c_void_p, ctypes.c_int64, _i64p, _i64p, _i64p, _f64p, ctypes.c_int64, _f64p, _f64p,
         _f64p, _f64p, ctypes.c_uint64, ctypes.c_uint64, _f64p, _f64p, _i32p, ctypes.c_uint32]),
+    "gf_sample_multi": (ctypes.c_int, [
+        ctypes.c_void_p, ctypes.c_int64, _i64p, _i64p, _i64p, _f64p, ctypes.c_int64, _f64p, _f64p,
+        _f64p, ctypes.c_int64, _f64p, ctypes.c_uint64, ctypes.c_uint64, _f64p, _f64p, _i32p, ctypes.c_uint32]),
+    "gf_loglike_multi": (ctypes.c_int, [
+        ctypes.c_void_p, ctypes.c_int64, _i64p, _i64p, _i64p, _f64p, ctypes.c_int64, _f64p, _f64p,
+        _f64p, ctypes.c_int64, _f64p, _f64p, _f64p, _i32p, ctypes.c_uint32]),
     "gf_factor_batched": (ctypes.c_int, [
         ctypes.c_void_p, ctypes.c_int64, _i64p, _i64p, _i64p, _i64p, _f64p, ctypes.c_int64, _f64p,
         _f64p, _f64p, _f64p, _f64p, _f64p, _i32p, ctypes.c_uint32]),
@@ -88,6 +94,12 @@ _SIGNATURES = {
     "gf_psd_batched": (ctypes.c_int, [
         ctypes.c_void_p, ctypes.c_int64, _i64p, _f64p, _f64p, _f64p, ctypes.c_int64, _f64p,
         ctypes.c_uint32]),
+    "gf_power_spectrum_batched": (ctypes.c_int, [
+        ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, _f64p, ctypes.c_double, ctypes.c_int, _f64p,
+        ctypes.c_uint32]),
+    "gf_bin_power_batched": (ctypes.c_int, [
+        ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _i64p, _i64p, _f64p, _f64p,
+        ctypes.c_double, _f64p, _f64p, ctypes.c_uint32]),
     "gf_conditional_mean": (ctypes.c_int, [
         ctypes.c_void_p, ctypes.c_int64, _f64p, ctypes.c_int64, _f64p, ctypes.c_int64, _f64p,
         _f64p, _f64p, ctypes.c_uint32]),
@@ -362,6 +374,53 @@ class Solver:
         self._order_after(flags, out, logdet, status)
         return out, logdet, status
 
+    # -- K1m / K2m: k right-hand sides per sequence on one factor ---------------------------
+    def sample_multi(self, kb, geom, t, k, diag=None, normals=None, seed=0, seq0=0, out=None, logdet=None,
+                     status=None, flags=0):
+        """k realisations per sequence from ONE factor -> (x[sum N * k] laid out [b][r][n], logdet[B],
+        status[B]).  ``normals`` (same layout) or Philox with realisation index seq0 + b k + r."""
+        B, k = geom.B, int(k)
+        assert kb.B == B and k >= 1
+        total = int(geom.n_off[-1])
+        keep = []
+        pt, q = _addr(t, count=geom.t_len, name="t"); keep.append(q)
+        pd, q = _addr(diag, count=total, name="diag"); keep.append(q)
+        pn_, q = _addr(normals, count=total * k, name="normals"); keep.append(q)
+        out, po = _out(out, (total * k,))
+        logdet, pl = _out(logdet, (B,))
+        status, ps = _out(status, (B,), np.int32)
+        n_off, pn = _i64(geom.n_off)
+        t_off, pto = _i64(geom.t_off)
+        j_off, pj = _i64(kb.j_off)
+        self._order_before(t, diag, normals, out, logdet, status)
+        self._check(self._lib.gf_sample_multi(
+            self._h, B, pn, pto, pj, pt, geom.t_len, pd, kb.coef.ctypes.data, kb.ddiag.ctypes.data, k,
+            pn_, int(seed), int(seq0), po, pl, ps, flags))
+        self._order_after(flags, out, logdet, status)
+        return out, logdet, status
+
+    def loglike_multi(self, kb, geom, t, y, k, diag=None, logdet=None, quad=None, status=None, flags=0):
+        """k data vectors per sequence on ONE factor -> (logdet[B], quad[B * k], status[B])."""
+        B, k = geom.B, int(k)
+        assert kb.B == B and k >= 1
+        total = int(geom.n_off[-1])
+        keep = []
+        pt, q = _addr(t, count=geom.t_len, name="t"); keep.append(q)
+        py, q = _addr(y, count=total * k, name="y"); keep.append(q)
+        pd, q = _addr(diag, count=total, name="diag"); keep.append(q)
+        logdet, pl = _out(logdet, (B,))
+        quad, pq = _out(quad, (B * k,))
+        status, ps = _out(status, (B,), np.int32)
+        n_off, pn = _i64(geom.n_off)
+        t_off, pto = _i64(geom.t_off)
+        j_off, pj = _i64(kb.j_off)
+        self._order_before(t, y, diag, logdet, quad, status)
+        self._check(self._lib.gf_loglike_multi(
+            self._h, B, pn, pto, pj, pt, geom.t_len, pd, kb.coef.ctypes.data, kb.ddiag.ctypes.data, k,
+            py, pl, pq, ps, flags))
+        self._order_after(flags, logdet, quad, status)
+        return logdet, quad, status
+
     # -- K3 ----------------------------------------------------------------------------
     def factor(self, kb, geom, t, diag=None, d=None, W=None, w_off=None, want_W=True, logdet=None,
                status=None, flags=0):
@@ -436,6 +495,32 @@ class Solver:
         self._order_after(flags, out)
         return out
 
+
+    # -- K7 ----------------------------------------------------------------------------
+    def power_spectrum(self, flux, B, N, d, include_zero=False, out=None, flags=0):
+        """-> power[B, N//2 (+1)] = |rfft(flux)|^2 d / sqrt(2 pi) / N (flux [B, N] in ppm, d in 1/uHz)."""
+        nout = N // 2 + 1 - (0 if include_zero else 1)
+        pf, keep = _addr(flux, count=B * N, name="flux")
+        out, po = _out(out, (B, nout))
+        self._order_before(flux, out)
+        self._check(self._lib.gf_power_spectrum_batched(self._h, B, N, pf, float(d), int(include_zero), po, flags))
+        self._order_after(flags, out)
+        return out
+
+    def bin_power(self, power, B, axis, lo, cnt, constant=1.0, stat=None, err=None, flags=0):
+        """-> (stat[B, nb], err[B, nb]) for bins [lo[k], lo[k] + cnt[k]) of the shared axis[F]."""
+        F = int(axis.numel()) if hasattr(axis, "numel") else int(np.size(axis))
+        lo_a, plo = _i64(lo)
+        cnt_a, pcnt = _i64(cnt)
+        nb = len(lo_a)
+        pa, k1 = _addr(axis, count=F, name="axis")
+        pp, k2 = _addr(power, count=B * F, name="power")
+        stat, ps = _out(stat, (B, nb))
+        err, pe = _out(err, (B, nb))
+        self._order_before(axis, power, stat, err)
+        self._check(self._lib.gf_bin_power_batched(self._h, B, F, nb, plo, pcnt, pa, pp, float(constant), ps, pe, flags))
+        self._order_after(flags, stat, err)
+        return stat, err
 
     # -- K6 ----------------------------------------------------------------------------
     def conditional_mean(self, coef, t, ts, alpha, out=None, flags=0):

@@ -119,6 +119,29 @@ int gf_sample_batched(gf_handle h, int64_t B, const int64_t *n_off, const int64_
                       uint64_t seq0, double *out, double *logdet /* nullable */,
                       int32_t *status, uint32_t flags);
 
+/* ---- K1m / K2m: k right-hand sides per sequence on ONE factor ----------------------------
+ * SURVEY.md 8b's `k` ("many y / many realisations per factor"): celerite2 factors once in
+ * compute() and then serves sample(size=k) (reference gadfly/gp.py:372-395, the (N, k) branch of
+ * np.random.randn) and repeated log_likelihood calls from the stored factor.  Here: one factor scan
+ * per sequence (d and W in library scratch, sum_b N_b J_b doubles of device memory), then ALL B k
+ * O(N J) sweeps in one launch, one CTA each, sharing the factor.
+ *   gf_sample_multi   out[b][r][:] = L_b (sqrt(d_b) o n_{b,r}),  r < k;  out / normals are laid out
+ *                     [b][r][n] (offset k n_off[b] + r N_b); normals == NULL draws n_{b,r} from
+ *                     Philox with the global realisation index seq0 + b k + r (gadfly_b200/philox.py)
+ *   gf_loglike_multi  quad[b][r] = z^T D^-1 z, z = L_b^-1 y_{b,r};  y laid out like out, quad is
+ *                     [B][k]; logdet[B] (nullable), status[B] as for the fused entry points
+ * For one realisation per factor the fused K1 / K2 are cheaper (nothing is stored). */
+int gf_sample_multi(gf_handle h, int64_t B, const int64_t *n_off, const int64_t *t_off,
+                    const int64_t *j_off, const double *t, int64_t t_len,
+                    const double *diag /* nullable */, const double *coef, const double *ddiag,
+                    int64_t k, const double *normals /* nullable */, uint64_t seed, uint64_t seq0,
+                    double *out, double *logdet /* nullable */, int32_t *status, uint32_t flags);
+int gf_loglike_multi(gf_handle h, int64_t B, const int64_t *n_off, const int64_t *t_off,
+                     const int64_t *j_off, const double *t, int64_t t_len,
+                     const double *diag /* nullable */, const double *coef, const double *ddiag,
+                     int64_t k, const double *y, double *logdet /* nullable */, double *quad,
+                     int32_t *status, uint32_t flags);
+
 /* ---- K3: factor, materialising d[N] (and W[N,J] if W != NULL) ----------------------
  * Replaces driver.factor where the factor itself is wanted (reference gadfly/gp.py:202-204
  * followed by apply_inverse / predict, gadfly/gp.py:370,232).  d is laid out like y;
@@ -149,6 +172,26 @@ int gf_sweep_batched(gf_handle h, int op, int64_t B, const int64_t *n_off, const
 int gf_psd_batched(gf_handle h, int64_t B, const int64_t *j_off, const double *coef_base,
                    const double *delta /* [B] */, const double *omega, int64_t F,
                    double *out /* [B][F] */, uint32_t flags);
+
+/* ---- K7: observed power spectrum and its binning (the other side of the round trip) ------
+ * Replaces PowerSpectrum._fft (reference gadfly/psd.py:566-587) and bin_power_spectrum with
+ * spectral_binning / spectral_binning_err (gadfly/psd.py:186-297) for B evenly sampled light curves
+ * at once, so that sample -> observed PSD -> binning -> comparison with gf_psd_batched stays on the
+ * device.  The transform is cuFFT (D2Z, bound with dlopen at first use; a positive cudaError is
+ * returned if libcufft is not installed); normalisation and binning are this library's kernels.
+ *   gf_power_spectrum_batched  power[b][i] = |rfft(flux_b)|_i^2 * d / sqrt(2 pi) / N, flux [B][N] in
+ *                              ppm, d = cadence in 1/uHz; i runs over N/2 + 1 frequencies
+ *                              (rfftfreq(N, d)), without the first one unless include_zero
+ *   gf_bin_power_batched       bins are index ranges [lo[k], lo[k] + cnt[k]) (HOST int64, from
+ *                              searchsorted of the bin edges) of the shared monotone axis[F] (log10 f
+ *                              or f); stat[b][k] = trapezoidal mean of power_b over the bin,
+ *                              err[b][k] = std / sqrt(n) * mean(axis) / span / constant; one-point bins
+ *                              return that point, empty bins NaN */
+int gf_power_spectrum_batched(gf_handle h, int64_t B, int64_t N, const double *flux, double d,
+                              int include_zero, double *power, uint32_t flags);
+int gf_bin_power_batched(gf_handle h, int64_t B, int64_t F, int64_t nb, const int64_t *lo,
+                         const int64_t *cnt, const double *axis, const double *power, double constant,
+                         double *stat, double *err, uint32_t flags);
 
 /* ---- K6: conditional mean at new times ------------------------------------------------
  * Replaces celerite2 driver.general_matmul_lower + general_matmul_upper as ConditionalDistribution

@@ -401,3 +401,107 @@ def test_gp_facade_matches_definition_golden(solver, name, tol_ld, tol_ll, tol_x
     gp = g.GaussianProcess(k, t=gd["t"], diag=diag)
     assert gp.log_likelihood(gd["y"]) == pytest.approx(float(gd["logl"]), rel=tol_ll)
     assert _maxrel(gp.apply_inverse(gd["y"]), gd["alpha"]) <= 10 * tol_x
+
+
+# ---- k right-hand sides per sequence on ONE factor (gf_sample_multi / gf_loglike_multi) -------------
+def test_multi_rhs_shares_one_factor(solver, solar_kernel, giant_kernel):
+    """SURVEY.md 8b's k: realisations / data vectors sharing a factor (celerite2 sample(size=k),
+    reference gadfly/gp.py:372-395).  Ragged batch of two kernels, k = 5: every realisation equals the
+    fused single-realisation kernel's and the oracle's for the same normal draws; Philox realisation
+    index seq0 + b k + r; log-likelihood pieces of k data vectors."""
+    rng = np.random.default_rng(17)
+    kernels = [solar_kernel, giant_kernel]
+    lengths = [700, 333]
+    k = 5
+    ts = [np.cumsum(6e-5 * (1 + 0.3 * rng.random(n))) for n in lengths]
+    t = np.concatenate(ts)
+    kb = KernelBatch(kernels)
+    geom = Geometry.ragged(lengths)
+    diag = np.concatenate([np.full(n, 25.0) for n in lengths])
+    nrm = [rng.standard_normal((k, n)) for n in lengths]
+    x, logdet, status = solver.sample_multi(kb, geom, t, k, diag=diag, normals=np.concatenate([a.ravel() for a in nrm]))
+    assert np.all(status == 0)
+    off = 0
+    ys = []
+    for b, (kern, n) in enumerate(zip(kernels, lengths)):
+        scan = kern.scan_coefficients()
+        xb = x[off:off + k * n].reshape(k, n)
+        off += k * n
+        for r in range(k):
+            ref, o_ld, st = oracle.stream(1, scan, ts[b], nrm[b][r], diag=np.full(n, 25.0))
+            assert st == 0 and _maxrel(xb[r], ref) <= RTOL
+            assert logdet[b] == pytest.approx(o_ld, rel=1e-11)
+        ys.append(xb)
+    # Philox draws: realisation (b, r) is sequence seq0 + b k + r of the host generator
+    xp, _, _ = solver.sample_multi(kb, geom, t, k, diag=diag, seed=5, seq0=100)
+    ref = oracle.stream(1, kernels[1].scan_coefficients(), ts[1], philox.normals(5, 100 + 1 * k + 3, lengths[1]),
+                        diag=np.full(lengths[1], 25.0))[0]
+    got = xp[k * lengths[0] + 3 * lengths[1]:k * lengths[0] + 4 * lengths[1]]
+    assert _maxrel(got, ref) <= RTOL
+    # k data vectors per sequence
+    y = np.concatenate([a.ravel() for a in ys])
+    logdet2, quad, status = solver.loglike_multi(kb, geom, t, y, k, diag=diag)
+    assert np.all(status == 0)
+    for b, (kern, n) in enumerate(zip(kernels, lengths)):
+        for r in range(k):
+            o_ld, o_q, st = oracle.stream(0, kern.scan_coefficients(), ts[b], ys[b][r], diag=np.full(n, 25.0))
+            assert quad[b * k + r] == pytest.approx(o_q, rel=RTOL)
+            assert logdet2[b] == pytest.approx(o_ld, rel=1e-11)
+    # the batch facade: [B, size, N]
+    xs, st = batch.sample([solar_kernel] * 3, np.arange(256) * 6e-5, size=4, seed=9, solver=solver, subtract_mean=False)
+    assert xs.shape == (3, 4, 256) and np.all(st == 0)
+    one, _ = batch.sample([solar_kernel], np.arange(256) * 6e-5, seed=9, seq0=2 * 4 + 1, solver=solver, subtract_mean=False)
+    assert _maxrel(xs[2, 1], one[0]) <= RTOL
+
+
+# ---- the observed power spectrum and its binning on the device (SURVEY.md 8f-3) ----------------------
+def test_observed_power_spectrum_and_binning_on_device(solver):
+    """gf_power_spectrum_batched / gf_bin_power_batched against the host restatement of the reference's
+    ``PowerSpectrum._fft`` (gadfly/psd.py:566-587: numpy rfft, norm d / sqrt(2 pi) / N) and
+    ``bin_power_spectrum`` (gadfly/psd.py:229-297), odd and even lengths, linear and log bins."""
+    from gadfly_b200 import psd as P
+    rng = np.random.default_rng(4)
+    for N in (4096, 10007):
+        flux = rng.standard_normal((3, N)) * 100.0 + 5 * np.sin(np.arange(N) * 0.01)[None, :]
+        d_days = 1.0 / 1440.0
+        freq, power, norm = P.power_spectra(flux, d_days, solver=solver)
+        for b in range(3):
+            ref = g.PowerSpectrum.from_light_curve(np.arange(N) * d_days, flux[b])
+            np.testing.assert_allclose(freq, ref.frequency, rtol=1e-14)
+            assert np.max(np.abs(power[b] - ref.power)) <= 1e-12 * np.max(ref.power)
+            assert norm == pytest.approx(ref.norm, rel=1e-15)
+        for log, bins in ((True, 15), (False, 40)):
+            fb, stat, err = P.bin_power_spectra(freq, power, bins=bins, log=log, solver=solver)
+            for b in range(3):
+                ref = P.bin_power_spectrum(g.PowerSpectrum(freq, power[b]), bins=bins, log=log)
+                np.testing.assert_allclose(fb, ref.frequency, rtol=1e-13)
+                np.testing.assert_allclose(stat[b], ref.power, rtol=1e-11, equal_nan=True)
+                np.testing.assert_allclose(err[b], ref.error, rtol=1e-9, equal_nan=True)
+
+
+def test_round_trip_stays_on_the_device(solver, solar_kernel):
+    """The reference's round trip (gadfly/tests/test_core.py:17-49) without leaving HBM: B Philox draws
+    from the fused sample kernel (CUDA tensor out) -> FFT power spectra -> 15 log bins -> the kernel PSD
+    at the bin centres, all through device pointers; binned spectra within 5 sigma of the model for
+    3 < f < 1000 uHz, as the reference asserts."""
+    import torch
+    from gadfly_b200 import psd as P
+    dev = torch.device("cuda", solver.device)
+    B, N = 6, 100_000
+    t_days = np.linspace(0, 100, N)
+    t = torch.as_tensor(t_days * 0.0864, device=dev)             # days -> 1/uHz (reference gadfly/gp.py:79-86)
+    x = torch.empty(B * N, dtype=torch.float64, device=dev)
+    kb = KernelBatch([solar_kernel] * B)
+    _, _, status = solver.sample(kb, Geometry.shared_t(B, N), t, seed=42, out=x)
+    assert np.all(status == 0)
+    flux = x.view(B, N)
+    flux = flux - flux.mean(dim=1, keepdim=True)                  # the reference's mean subtraction (gp.py:392)
+    freq, power, _ = P.power_spectra(flux.contiguous(), float(t_days[1] - t_days[0]), solver=solver)
+    assert power.is_cuda
+    fb, stat, err = P.bin_power_spectra(freq, power, bins=15, solver=solver)
+    assert stat.is_cuda
+    model = solver.psd(KernelBatch([solar_kernel]), torch.as_tensor(2 * np.pi * fb, device=dev),
+                       out=torch.empty((1, len(fb)), dtype=torch.float64, device=dev))
+    ok = torch.as_tensor((fb < 1e3) & (fb > 3), device=dev)
+    dev_sigma = ((model[0][None, :] - stat).abs() / torch.nan_to_num(err, nan=0.0).max(dim=1, keepdim=True).values)[:, ok]
+    assert float(dev_sigma.max()) < 5

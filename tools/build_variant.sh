@@ -6,5 +6,5 @@ cd "$(dirname "$0")/.."
 name=$1; shift
 mkdir -p variants
 nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -shared "$@" \
-    -o variants/libgadfly_b200_$name.so gadfly_b200/csrc/*.cu
+    -o variants/libgadfly_b200_$name.so gadfly_b200/csrc/*.cu -ldl
 echo variants/libgadfly_b200_$name.so
