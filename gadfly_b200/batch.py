@@ -13,7 +13,7 @@ import numpy as np
 
 from .solver import Geometry, KernelBatch, default_solver
 
-__all__ = ['log_likelihood', 'sample', 'shard_bounds', 'shard', 'gather_concat']
+__all__ = ['log_likelihood', 'log_likelihood_gradient', 'sample', 'shard_bounds', 'shard', 'gather_concat']
 
 _LOG_2PI = float(np.log(2 * np.pi))
 
@@ -62,6 +62,45 @@ def log_likelihood(kernels, t, y, diag=None, lengths=None, mean=0.0, quiet=True,
     if return_parts:
         return ll, logdet, quad, status
     return ll
+
+
+def log_likelihood_gradient(S0, w0, Q, delta, t, y, diag=None, wrt=('S0', 'w0', 'Q'), rel_step=2e-3,
+                            solver=None, return_value=False):
+    """Gradient of log L with respect to the SHO hyper-parameters of every term, ``d logL / d ln p``
+    for p in (S0_j, w0_j, Q_j) -- what a fit of the kernel to a light curve needs (the reference fits
+    with celerite2.jax + BFGS: notebooks/virgo_lc.ipynb:48).
+
+    Method: NOT an adjoint sweep.  The fused log-likelihood kernel runs one sequence per SM, so a
+    single light curve leaves 147 of 148 SMs idle; here every hyper-parameter gets four perturbed
+    kernels (p (1 +- h), p (1 +- 2h): fourth-order central differences in ln p) and all 4 P + 1
+    kernels are scanned in ONE batched launch against the one light curve (``FLAG_SHARED_Y``: y is
+    passed once).  For the solar kernel's 258 parameters that is 1033 sequences = 7 waves of 148, the
+    wall time of ~7 single log-likelihoods -- what an O(N J^2) adjoint pass on one SM would cost too.
+    Accuracy: truncation h^4, rounding ~1e-12 |log L| / h: ~1e-6 of the gradient's norm at the
+    default step (tests/test_gpu_parity.py checks it against a longdouble evaluation of the kernel
+    definition).  Returns ``grad[len(wrt), J/2]`` (and log L at the centre with ``return_value``)."""
+    from .feeder import HyperparameterBatch, kernel_batch_from_sho
+    from .solver import FLAG_SHARED_Y
+    S0, w0, Q = (np.ascontiguousarray(v, dtype=np.float64) for v in (S0, w0, Q))
+    nt = len(S0)
+    names = list(wrt)
+    P = len(names) * nt
+    steps = np.array([-2.0, -1.0, 1.0, 2.0]) * rel_step
+    rows = 4 * P + 1
+    par = {'S0': np.tile(S0, (rows, 1)), 'w0': np.tile(w0, (rows, 1)), 'Q': np.tile(Q, (rows, 1))}
+    for i, name in enumerate(names):
+        for j in range(nt):
+            r0 = 1 + 4 * (i * nt + j)
+            par[name][r0:r0 + 4, j] *= np.exp(steps)
+    hpb = HyperparameterBatch(par['S0'].ravel(), par['w0'].ravel(), par['Q'].ravel(),
+                              np.arange(rows + 1, dtype=np.int64) * nt)
+    kb = kernel_batch_from_sho(hpb, delta)
+    solver = solver or default_solver()
+    ll = log_likelihood(kb, t, y, diag, solver=solver, flags=FLAG_SHARED_Y)
+    f = ll[1:].reshape(P, 4)
+    grad = (f[:, 0] - 8 * f[:, 1] + 8 * f[:, 2] - f[:, 3]) / (12 * rel_step)
+    grad = grad.reshape(len(names), nt)
+    return (grad, float(ll[0])) if return_value else grad
 
 
 def sample(kernels, t, diag=None, lengths=None, normals=None, seed=0, seq0=0, solver=None,

@@ -505,3 +505,24 @@ def test_round_trip_stays_on_the_device(solver, solar_kernel):
     ok = torch.as_tensor((fb < 1e3) & (fb > 3), device=dev)
     dev_sigma = ((model[0][None, :] - stat).abs() / torch.nan_to_num(err, nan=0.0).max(dim=1, keepdim=True).values)[:, ok]
     assert float(dev_sigma.max()) < 5
+
+
+# ---- gradients of log L with respect to (S0, w0, Q) ---------------------------------
+def test_log_likelihood_gradient_vs_definition(solver):
+    """batch.log_likelihood_gradient (4 P + 1 perturbed kernels scanned in one batched launch against the
+    one light curve) against tests/golden/def_grad.npz: d log L / d ln p by central differences of the
+    longdouble kernel DEFINITION (tools/make_golden_definition.py), 6 terms x (S0, w0, Q)."""
+    gd = golden("def_grad.npz")
+    grad, ll = batch.log_likelihood_gradient(gd["S0"], gd["w0"], gd["Q"], float(gd["delta"]), gd["t"], gd["y"],
+                                             diag=gd["diag"], solver=solver, return_value=True)
+    assert ll == pytest.approx(float(gd["logl"]), rel=RTOL)
+    ref = gd["grad"]
+    assert grad.shape == ref.shape == (3, 6)
+    assert np.max(np.abs(grad - ref)) <= 1e-6 * np.linalg.norm(ref)
+    # every component that matters individually, too
+    big = np.abs(ref) > 1e-3 * np.max(np.abs(ref))
+    np.testing.assert_allclose(grad[big], ref[big], rtol=1e-5)
+    # a subset of the parameters
+    g_w0 = batch.log_likelihood_gradient(gd["S0"], gd["w0"], gd["Q"], float(gd["delta"]), gd["t"], gd["y"],
+                                         diag=gd["diag"], wrt=("w0",), solver=solver)
+    np.testing.assert_allclose(g_w0[0], grad[1], rtol=1e-12)

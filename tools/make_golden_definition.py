@@ -160,8 +160,57 @@ def make_case(name, star, delta, step_log2, index, yerr, seed):
           f"min pivot {float(np.min(np.diag(L)) ** 2):.4g}")
 
 
+def logl_definition(S0, w0, Q, delta, index, step_log2, diag, y):
+    """log L from the definition in longdouble (inputs may be longdouble arrays)."""
+    n = len(index)
+    dt = LD(2.0) ** step_log2
+    max_lag = int(index[-1] - index[0])
+    table = exposure_kernel(np.arange(max_lag + 1).astype(LD) * dt, S0, w0, Q, delta)
+    K = table[np.abs(index[:, None] - index[None, :])]
+    K[np.arange(n), np.arange(n)] += np.asarray(diag, dtype=LD)
+    L = cholesky_ld(K)
+    z = solve_lower_ld(L, np.asarray(y, dtype=LD))
+    return -(z @ z + 2 * np.sum(np.log(np.diag(L))) + n * np.log(2 * LD(np.pi))) / 2
+
+
+def make_gradient_case(name, seed):
+    """d log L / d ln(S0_j, w0_j, Q_j) of a 6-term kernel (3 granulation-like, 3 p-mode-like terms) by
+    central differences of the longdouble definition (h = 1e-5: truncation ~1e-10, rounding ~1e-11)."""
+    rng = np.random.default_rng(seed)
+    S0 = np.array([900.0, 12.0, 0.6, 2.0e-3, 3.5e-3, 1.2e-3])
+    w0 = np.array([7.0, 120.0, 900.0, 17000.0, 19500.0, 21500.0])
+    Q = np.array([0.6, 0.6, 0.7, 400.0, 650.0, 300.0])
+    delta, step_log2, n = 2e-4, -12, 256
+    index = np.arange(n)
+    t = index * 2.0 ** step_log2
+    diag = np.full(n, 4.0)
+    # data: a draw from the model
+    table = exposure_kernel(np.arange(n).astype(LD) * LD(2.0) ** step_log2, S0, w0, Q, delta)
+    K = table[np.abs(index[:, None] - index[None, :])]
+    K[np.arange(n), np.arange(n)] += diag.astype(LD)
+    y = np.asarray(cholesky_ld(K) @ rng.standard_normal(n).astype(LD), dtype=np.float64)
+    h = LD(1e-5)
+    base = [np.asarray(v, dtype=LD) for v in (S0, w0, Q)]
+    grad = np.zeros((3, len(S0)))
+    for i in range(3):
+        for j in range(len(S0)):
+            vals = []
+            for sgn in (-1, 1):
+                p = [v.copy() for v in base]
+                p[i][j] = p[i][j] * np.exp(sgn * h)
+                vals.append(logl_definition(p[0], p[1], p[2], delta, index, step_log2, diag, y))
+            grad[i, j] = float((vals[1] - vals[0]) / (2 * h))
+    logl = float(logl_definition(base[0], base[1], base[2], delta, index, step_log2, diag, y))
+    np.savez(os.path.join(OUT, name + ".npz"), S0=S0, w0=w0, Q=Q, delta=delta, t=t, diag=diag, y=y,
+             logl=logl, grad=grad)
+    print(f"{name}: log L = {logl:.10g}, |grad| = {np.linalg.norm(grad):.6g}")
+    print(np.array2string(grad, precision=6))
+
+
 def main():
-    which = sys.argv[1:] or ["def_solar_200s", "def_subgiant", "def_giant", "def_solar_sc"]
+    which = sys.argv[1:] or ["def_solar_200s", "def_subgiant", "def_giant", "def_solar_sc", "def_grad"]
+    if "def_grad" in which:
+        make_gradient_case("def_grad", 21)
     if "def_solar_200s" in which:
         make_case("def_solar_200s", "Sun", 2e-4, -12, np.arange(1024), None, 11)
     if "def_subgiant" in which:
