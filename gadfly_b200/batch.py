@@ -76,29 +76,34 @@ def log_likelihood_gradient(S0, w0, Q, delta, t, y, diag=None, wrt=('S0', 'w0', 
     kernels are scanned in ONE batched launch against the one light curve (``FLAG_SHARED_Y``: y is
     passed once).  For the solar kernel's 258 parameters that is 1033 sequences = 7 waves of 148, the
     wall time of ~7 single log-likelihoods -- what an O(N J^2) adjoint pass on one SM would cost too.
-    Accuracy: truncation h^4, rounding ~1e-12 |log L| / h: ~1e-6 of the gradient's norm at the
-    default step (tests/test_gpu_parity.py checks it against a longdouble evaluation of the kernel
-    definition).  Returns ``grad[len(wrt), J/2]`` (and log L at the centre with ``return_value``)."""
+    Steps: ``rel_step`` in ln p, except ln w0 of a resonant term, where log L varies on the scale
+    of the line width 1 / Q: h = min(rel_step, 0.05 / Q_j).  Accuracy: truncation ~h^4, rounding
+    ~1e-12 |log L| / h: ~1e-6 of the gradient's norm (tests/test_gpu_parity.py checks it against a
+    longdouble evaluation of the kernel definition).  Returns ``grad[len(wrt), J/2]`` (and log L at the centre with ``return_value``)."""
     from .feeder import HyperparameterBatch, kernel_batch_from_sho
     from .solver import FLAG_SHARED_Y
     S0, w0, Q = (np.ascontiguousarray(v, dtype=np.float64) for v in (S0, w0, Q))
     nt = len(S0)
     names = list(wrt)
     P = len(names) * nt
-    steps = np.array([-2.0, -1.0, 1.0, 2.0]) * rel_step
+    stencil = np.array([-2.0, -1.0, 1.0, 2.0])
+    h = np.full((len(names), nt), float(rel_step))
+    for i, name in enumerate(names):
+        if name == 'w0':
+            h[i] = np.minimum(rel_step, 0.05 / np.maximum(Q, 0.5))
     rows = 4 * P + 1
     par = {'S0': np.tile(S0, (rows, 1)), 'w0': np.tile(w0, (rows, 1)), 'Q': np.tile(Q, (rows, 1))}
     for i, name in enumerate(names):
         for j in range(nt):
             r0 = 1 + 4 * (i * nt + j)
-            par[name][r0:r0 + 4, j] *= np.exp(steps)
+            par[name][r0:r0 + 4, j] *= np.exp(stencil * h[i, j])
     hpb = HyperparameterBatch(par['S0'].ravel(), par['w0'].ravel(), par['Q'].ravel(),
                               np.arange(rows + 1, dtype=np.int64) * nt)
     kb = kernel_batch_from_sho(hpb, delta)
     solver = solver or default_solver()
     ll = log_likelihood(kb, t, y, diag, solver=solver, flags=FLAG_SHARED_Y)
     f = ll[1:].reshape(P, 4)
-    grad = (f[:, 0] - 8 * f[:, 1] + 8 * f[:, 2] - f[:, 3]) / (12 * rel_step)
+    grad = (f[:, 0] - 8 * f[:, 1] + 8 * f[:, 2] - f[:, 3]) / (12 * h.ravel())
     grad = grad.reshape(len(names), nt)
     return (grad, float(ll[0])) if return_value else grad
 

@@ -139,4 +139,4 @@ def test_sharded_legs_two_gpus_nccl_gather():
     line = json.loads([ln for ln in p.stdout.splitlines() if ln.startswith("{")][-1])
     assert line["n_gpus"] == 2
     assert "NCCL" in line["cfg4"]["gather"]["collective"] and "bit-identical" in line["cfg4"]["gather"]["verified"]
-    assert line["cfg5"]["max_rel_vs_closed_form"] < 1e-8
+    assert line["cfg5"]["max_rel_vs_closed_form"] < 1e-6

@@ -175,7 +175,8 @@ def logl_definition(S0, w0, Q, delta, index, step_log2, diag, y):
 
 def make_gradient_case(name, seed):
     """d log L / d ln(S0_j, w0_j, Q_j) of a 6-term kernel (3 granulation-like, 3 p-mode-like terms) by
-    central differences of the longdouble definition (h = 1e-5: truncation ~1e-10, rounding ~1e-11)."""
+    central differences of the longdouble definition (h = 1e-7 in ln p: truncation (h Q)^2 / 6 < 1e-9 even
+    for ln w0 of the Q = 650 term, rounding ~1e-19 |log L| / h ~ 1e-9 absolute)."""
     rng = np.random.default_rng(seed)
     S0 = np.array([900.0, 12.0, 0.6, 2.0e-3, 3.5e-3, 1.2e-3])
     w0 = np.array([7.0, 120.0, 900.0, 17000.0, 19500.0, 21500.0])
@@ -189,7 +190,7 @@ def make_gradient_case(name, seed):
     K = table[np.abs(index[:, None] - index[None, :])]
     K[np.arange(n), np.arange(n)] += diag.astype(LD)
     y = np.asarray(cholesky_ld(K) @ rng.standard_normal(n).astype(LD), dtype=np.float64)
-    h = LD(1e-5)
+    h = LD(1e-7)
     base = [np.asarray(v, dtype=LD) for v in (S0, w0, Q)]
     grad = np.zeros((3, len(S0)))
     for i in range(3):
