@@ -20,12 +20,15 @@ cudaError_t launch_scan_fast(int mode, const ScanArgs &args, int jmax, int sm_co
                              cudaStream_t stream, int *launches);
 bool scan_fast_supports(int mode, int jmax);
 bool scan_small_supports(int mode, int jmax);
+bool scan_wide_supports(int jmax);
+size_t scan_wide_state_bytes(int grid);
+cudaError_t launch_scan_wide(int mode, const ScanArgs &args, int grid, double *state, cudaStream_t stream);
 cudaError_t launch_scan_small(int mode, const ScanArgs &args, int jmax, int sm_count,
                               cudaStream_t stream, int *launches);
 cudaError_t launch_sweep(int op, int64_t B, const int64_t *n_off, const int64_t *t_off,
                          const int64_t *j_off, const int64_t *w_off, const double *t,
                          const double *coef, const double *W, const double *Y, double *Z,
-                         cudaStream_t stream);
+                         int jc_max, cudaStream_t stream);
 cudaError_t launch_psd(int64_t B, const int64_t *j_off, const double *coef, const double *delta,
                        const double *omega, int64_t F, double *out, cudaStream_t stream);
 cudaError_t measure_fp64_peak(int sm_count, cudaStream_t stream, double *flops);
@@ -56,7 +59,7 @@ enum Slot {
     S_MD, S_MW, S_MZ, S_MT, S_MDIAG, S_MCOEF, S_MDDIAG, S_VNOFF, S_VTOFF, S_VJOFF, S_VWOFF, S_VDOFF, S_VCOEF,
     S_MY, S_MOUT, S_MQUAD,
     // observed power spectrum
-    S_FLUX, S_SPEC, S_POWER, S_BLO, S_BCNT, S_BAXIS, S_BSTAT, S_BERR, N_SLOTS
+    S_FLUX, S_SPEC, S_POWER, S_BLO, S_BCNT, S_BAXIS, S_BSTAT, S_BERR, S_WIDE, N_SLOTS
 };
 
 // A staging buffer and the event of its last use (a kernel reading / writing it on the compute
@@ -288,7 +291,7 @@ int check_geometry(gf_handle h, int64_t B, const int64_t *n_off, const int64_t *
         int64_t Jc = j_off[b + 1] - j_off[b];
         if (N < 0 || Jc < 0) return fail(h, GF_E_ARG, "offsets must be non-decreasing");
         if (N > 0x7fffff00LL) return fail(h, GF_E_ARG, "a sequence is limited to 2^31 - 256 samples");
-        if (2 * Jc > GF_MAX_J) return fail(h, GF_E_TOO_WIDE, "state wider than GF_MAX_J");
+        if (2 * Jc > GF_MAX_J_WIDE) return fail(h, GF_E_TOO_WIDE, "state wider than GF_MAX_J_WIDE");
         if (t_off[b] < 0 || t_off[b] + N > t_len) return fail(h, GF_E_ARG, "t_off out of range");
         g->jmax = std::max(g->jmax, (int)(2 * Jc));
         cost[(size_t)b] = (double)N * (double)(4 * Jc * Jc + 8);
@@ -373,7 +376,14 @@ int run_scan(gf_handle h, int mode, int64_t B, const int64_t *n_off, const int64
     {
         Timer timer(h);
         const bool ref = (flags & GF_FLAG_REFERENCE_ORDER) || !gf::scan_fast_supports(mode, g.jmax);
-        if (ref) {
+        if (g.jmax > GF_MAX_J) {
+            // wider than the register-resident kernels take: state in L2-resident global scratch
+            const int grid = (int)std::min<int64_t>(B, (int64_t)h->sm_count);
+            void *state = nullptr;
+            GF_CUDA(h, reserve(h, S_WIDE, gf::scan_wide_state_bytes(grid), &state));
+            GF_CUDA(h, gf::launch_scan_wide(mode, A, grid, (double *)state, h->stream));
+            h->launches += 1;
+        } else if (ref) {
             int grid = (int)std::min<int64_t>(B, (int64_t)h->sm_count);
             GF_CUDA(h, gf::launch_scan_ref(mode, A, grid, h->stream));
             h->launches += 1;
@@ -591,7 +601,7 @@ int gf_sweep_batched(gf_handle h, int op, int64_t B, const int64_t *n_off, const
     {
         Timer timer(h);
         GF_CUDA(h, gf::launch_sweep(op, B, d_noff, d_toff, d_joff, d_woff, d_t, d_coef, d_W, d_Y,
-                                    o_z.dev, h->stream));
+                                    o_z.dev, g.jmax / 2, h->stream));
         h->launches += 1;
     }
     GF_CUDA(h, end_kernel(h));
@@ -756,7 +766,7 @@ int run_multi(gf_handle h, int mode, int64_t B, const int64_t *n_off, const int6
         {
             Timer timer(h);
             GF_CUDA(h, gf::launch_multi_prep(V, max_n, d_vn, d_vd, (const double *)d_d, d_in, seed, seq0, o.dev, h->stream));
-            GF_CUDA(h, gf::launch_sweep(1, V, d_vn, d_vt, d_vj, d_vw, d_t, d_vcoef, (const double *)d_W, o.dev, o.dev, h->stream));
+            GF_CUDA(h, gf::launch_sweep(1, V, d_vn, d_vt, d_vj, d_vw, d_t, d_vcoef, (const double *)d_W, o.dev, o.dev, g.jmax / 2, h->stream));
             h->launches += 2;
         }
         GF_CUDA(h, end_kernel(h));
@@ -770,7 +780,7 @@ int run_multi(gf_handle h, int mode, int64_t B, const int64_t *n_off, const int6
         GF_CUDA(h, begin_kernel(h));
         {
             Timer timer(h);
-            GF_CUDA(h, gf::launch_sweep(0, V, d_vn, d_vt, d_vj, d_vw, d_t, d_vcoef, (const double *)d_W, d_in, (double *)d_z, h->stream));
+            GF_CUDA(h, gf::launch_sweep(0, V, d_vn, d_vt, d_vj, d_vw, d_t, d_vcoef, (const double *)d_W, d_in, (double *)d_z, g.jmax / 2, h->stream));
             GF_CUDA(h, gf::launch_multi_quad(V, d_vn, d_vd, (const double *)d_d, (const double *)d_z, oq.dev, h->stream));
             h->launches += 2;
         }

@@ -38,10 +38,11 @@ constexpr int SW2_RS = 16;                        // ring slots (two halves)
 // consecutive steps of a warp must be at most two ring halves apart.
 static_assert(SW2_PROD <= SW2_RS, "producer stride must not exceed the ring");
 constexpr int SW2_HALF = 8;
-constexpr int SW2_TPL = 3;                        // terms per lane (3 x 32 >= GF_MAX_J / 2)
-constexpr int SW2_JC = 96;
-
+// terms per lane: 3 (3 x 32 >= GF_MAX_J / 2) -- or 6 for the wide kernels (6 x 32 >= GF_MAX_J_WIDE / 2),
+// a separate instantiation so that the ordinary widths keep their code
+template <int SW2_TPL>
 struct Sweep2Smem {
+    static constexpr int SW2_JC = 32 * SW2_TPL;
     double2 dot[SW2_RS][SW2_JC];     // row the state is read through at this step (U_n lower, W_n upper)
     double2 upd[SW2_RS][SW2_JC];     // row that enters the state after this step (W_n lower, U_n upper)
     double dec[SW2_RS][SW2_JC];      // decay of the state over the step into this one
@@ -74,7 +75,7 @@ __device__ __forceinline__ void sw_mbar_wait(unsigned long long *mb, uint32_t pa
         "}\n" ::"r"((uint32_t)__cvta_generic_to_shared(mb)), "r"(parity) : "memory");
 }
 
-template <bool UPPER, bool SOLVE>
+template <bool UPPER, bool SOLVE, int SW2_TPL>
 __global__ void __launch_bounds__(SW2_THREADS)
 sweep2_kernel(int64_t B, const int64_t *__restrict__ n_off, const int64_t *__restrict__ t_off,
               const int64_t *__restrict__ j_off, const int64_t *__restrict__ w_off,
@@ -82,7 +83,7 @@ sweep2_kernel(int64_t B, const int64_t *__restrict__ n_off, const int64_t *__res
               const double *__restrict__ W_all, const double *Y_all, double *Z_all)
 {
     extern __shared__ __align__(16) unsigned char sw2_raw[];
-    Sweep2Smem &sm = *reinterpret_cast<Sweep2Smem *>(sw2_raw);
+    Sweep2Smem<SW2_TPL> &sm = *reinterpret_cast<Sweep2Smem<SW2_TPL> *>(sw2_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
@@ -215,37 +216,44 @@ sweep2_kernel(int64_t B, const int64_t *__restrict__ n_off, const int64_t *__res
     }
 }
 
+template <int TPL>
+static cudaError_t launch_sweep_tpl(int op, int64_t B, const int64_t *n_off, const int64_t *t_off,
+                                    const int64_t *j_off, const int64_t *w_off, const double *t,
+                                    const double *coef, const double *W, const double *Y, double *Z,
+                                    cudaStream_t stream)
+{
+    const int grid = (int)(B < 65535 ? B : 65535);
+    static bool configured[64] = {};      // per device: a process may hold handles on several
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int bytes = (int)sizeof(Sweep2Smem<TPL>);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(sweep2_kernel<false, true, TPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(sweep2_kernel<false, false, TPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(sweep2_kernel<true, true, TPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(sweep2_kernel<true, false, TPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
+    switch (op) {
+    case 0: sweep2_kernel<false, true, TPL><<<grid, SW2_THREADS, bytes, stream>>>(B, n_off, t_off, j_off, w_off, t, coef, W, Y, Z); break;
+    case 1: sweep2_kernel<false, false, TPL><<<grid, SW2_THREADS, bytes, stream>>>(B, n_off, t_off, j_off, w_off, t, coef, W, Y, Z); break;
+    case 2: sweep2_kernel<true, true, TPL><<<grid, SW2_THREADS, bytes, stream>>>(B, n_off, t_off, j_off, w_off, t, coef, W, Y, Z); break;
+    default: sweep2_kernel<true, false, TPL><<<grid, SW2_THREADS, bytes, stream>>>(B, n_off, t_off, j_off, w_off, t, coef, W, Y, Z); break;
+    }
+    return cudaGetLastError();
+}
+
 }  // namespace
 
+// jc_max: most complex terms of any sequence of the batch
 cudaError_t launch_sweep(int op, int64_t B, const int64_t *n_off, const int64_t *t_off,
                          const int64_t *j_off, const int64_t *w_off, const double *t,
                          const double *coef, const double *W, const double *Y, double *Z,
-                         cudaStream_t stream)
+                         int jc_max, cudaStream_t stream)
 {
-    const int grid = (int)(B < 65535 ? B : 65535);
-    {
-        static bool configured[64] = {};      // per device: a process may hold handles on several
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (dev < 0 || dev >= 64 || !configured[dev]) {
-            cudaError_t e = cudaSuccess;
-            const int bytes = (int)sizeof(Sweep2Smem);
-            e = cudaFuncSetAttribute(sweep2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(sweep2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(sweep2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(sweep2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-            if (e != cudaSuccess) return e;
-            if (dev >= 0 && dev < 64) configured[dev] = true;
-        }
-        const size_t smem = sizeof(Sweep2Smem);
-        switch (op) {
-        case 0: sweep2_kernel<false, true><<<grid, SW2_THREADS, smem, stream>>>(B, n_off, t_off, j_off, w_off, t, coef, W, Y, Z); break;
-        case 1: sweep2_kernel<false, false><<<grid, SW2_THREADS, smem, stream>>>(B, n_off, t_off, j_off, w_off, t, coef, W, Y, Z); break;
-        case 2: sweep2_kernel<true, true><<<grid, SW2_THREADS, smem, stream>>>(B, n_off, t_off, j_off, w_off, t, coef, W, Y, Z); break;
-        default: sweep2_kernel<true, false><<<grid, SW2_THREADS, smem, stream>>>(B, n_off, t_off, j_off, w_off, t, coef, W, Y, Z); break;
-        }
-        return cudaGetLastError();
-    }
+    if (jc_max <= 96) return launch_sweep_tpl<3>(op, B, n_off, t_off, j_off, w_off, t, coef, W, Y, Z, stream);
+    return launch_sweep_tpl<6>(op, B, n_off, t_off, j_off, w_off, t, coef, W, Y, Z, stream);
 }
 
 }  // namespace gf

@@ -129,15 +129,15 @@ def kernel_batch_from_sho(hpb, delta, eps=1e-5):
     SHOTerm -> (a, b, c, d) (underdamped branch; gadfly only produces Q >= 0.5) and the
     exposure-time transform + diagonal correction (A.4) in the expression order of
     ``terms.TermConvolution`` -- it is cancellation-sensitive."""
-    from .solver import KernelBatch, GF_MAX_J
+    from .solver import KernelBatch, GF_MAX_J_WIDE
     S0, w0, Q, j_off = hpb.S0, hpb.w0, hpb.Q, hpb.j_off
     B = len(j_off) - 1
     if np.any(Q < 0.5):
         raise ValueError("overdamped terms (Q < 0.5): build those kernels per star")
     delta = np.broadcast_to(np.asarray(delta, dtype=np.float64), (B,)).copy()
     widths = np.diff(j_off)
-    if B and int(widths.max()) * 2 > GF_MAX_J:
-        raise ValueError(f"kernel state wider than GF_MAX_J = {GF_MAX_J}")
+    if B and int(widths.max()) * 2 > GF_MAX_J_WIDE:
+        raise ValueError(f"kernel state wider than GF_MAX_J_WIDE = {GF_MAX_J_WIDE}")
     f = np.sqrt(np.maximum(4.0 * Q ** 2 - 1.0, eps))
     a = S0 * w0 * Q
     b = a / f

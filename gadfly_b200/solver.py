@@ -28,7 +28,8 @@ import numpy as np
 __all__ = ["Solver", "KernelBatch", "SolverUnavailable", "LinAlgError", "default_solver",
            "library_path", "GF_MAX_J", "FLAG_ASYNC", "FLAG_REFERENCE_ORDER"]
 
-GF_MAX_J = 176
+GF_MAX_J = 176          # widest state of the register-resident scans
+GF_MAX_J_WIDE = 352     # widest state at all (slower kernel, state in L2-resident scratch)
 FLAG_ASYNC = 1
 FLAG_REFERENCE_ORDER = 2
 FLAG_SHARED_Y = 4
@@ -196,8 +197,8 @@ class KernelBatch:
         self.j_off = np.asarray(j_off, dtype=np.int64)
         self.ddiag = np.asarray(ddiag, dtype=np.float64)
         self.delta = np.asarray(delta, dtype=np.float64)
-        if self.B and int(np.max(np.diff(self.j_off))) * 2 > GF_MAX_J:
-            raise ValueError(f"kernel state wider than GF_MAX_J = {GF_MAX_J}")
+        if self.B and int(np.max(np.diff(self.j_off))) * 2 > GF_MAX_J_WIDE:
+            raise ValueError(f"kernel state wider than GF_MAX_J_WIDE = {GF_MAX_J_WIDE}")
 
     @staticmethod
     def for_stars(mass, radius, temperature, luminosity, texp_s=60.0, bandpass='SOHO VIRGO', alpha=None):

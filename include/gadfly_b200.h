@@ -60,8 +60,12 @@ enum {
     GF_E_NOMEM = -4
 };
 
-/* widest state the register-resident scan supports (22 blocks of 8) */
+/* widest state the register-resident scans support (22 blocks of 8) */
 #define GF_MAX_J 176
+/* widest state at all: batches containing a kernel with GF_MAX_J < J <= GF_MAX_J_WIDE (the solar kernel
+ * plus up to 90 extra terms, reference gadfly/core.py:405-427) run on a slower kernel whose state lives
+ * in L2-resident global scratch; the stored-factor sweeps (K4) take any width up to this one too */
+#define GF_MAX_J_WIDE 352
 
 /* flags */
 #define GF_FLAG_ASYNC 1u          /* do not synchronise before returning */

@@ -7,6 +7,7 @@ import pytest
 
 import gadfly_b200 as g
 from gadfly_b200 import batch
+from gadfly_b200.solver import Geometry, KernelBatch
 import oracle
 
 pytestmark = pytest.mark.gpu
@@ -228,3 +229,47 @@ def test_rounded_phase_regressions(solver, solar_kernel):
         sc = k.scan_coefficients()
         _check(solver, k, 2.1e5 + np.cumsum(np.full(300, 6e-5)), diag=1e-3 * (np.sum(sc[2]) + sc[6]), seed=nterm)
     _check(solver, solar_kernel, 2.1e5 + np.cumsum(np.full(1500, 6e-5)), diag=25.0, seed=9)
+
+
+def test_kernels_wider_than_the_register_resident_scans(solver, solar_kernel):
+    """``kernel + more terms`` (reference gadfly/core.py:405-427) beyond J = 176: the solar kernel plus
+    10 / 60 extra SHO terms (J = 192 / 292) runs on the wide kernel (state in L2-resident scratch) --
+    fused log-likelihood, fused sample and the stored-factor API (factor + sweeps with six terms per
+    lane), against the oracle at the north star's 1e-9; a batch mixing narrow and wide kernels; and
+    beyond GF_MAX_J_WIDE the library still refuses."""
+    rng = np.random.default_rng(8)
+    N = 300
+    t = np.cumsum(6e-5 * (1 + 0.2 * rng.random(N)))
+    for extra in (10, 60):
+        terms = list(solar_kernel.term.terms) + [
+            g.SHOTerm(S0=float(10 ** rng.uniform(-1, 1)), w0=float(10 ** rng.uniform(1, 4)), Q=float(10 ** rng.uniform(0, 2.5)))
+            for _ in range(extra)]
+        k = g.StellarOscillatorKernel(terms=terms, delta=solar_kernel.delta)
+        assert k.J == 172 + 2 * extra
+        scan = k.scan_coefficients()
+        nrm = rng.standard_normal(N)
+        x_ref, o_ld, st = oracle.stream(1, scan, t, nrm, diag=np.full(N, 9.0))
+        assert st == 0
+        kb = KernelBatch([k, solar_kernel])
+        geom = Geometry.shared_t(2, N)
+        diag = np.full(2 * N, 9.0)
+        x, logdet, status = solver.sample(kb, geom, t, diag, normals=np.concatenate([nrm, nrm]))
+        assert status.tolist() == [0, 0]
+        assert np.max(np.abs(x[:N] - x_ref)) <= 1e-9 * np.max(np.abs(x_ref))
+        assert logdet[0] == pytest.approx(o_ld, rel=1e-11)
+        # the narrow kernel in the same batch
+        x_sun = oracle.stream(1, solar_kernel.scan_coefficients(), t, nrm, diag=np.full(N, 9.0))[0]
+        assert np.max(np.abs(x[N:] - x_sun)) <= 1e-9 * np.max(np.abs(x_sun))
+        logdet2, quad, status = solver.loglike(kb, geom, t, np.concatenate([x_ref, x_sun]), diag)
+        o_ld2, o_q, _ = oracle.stream(0, scan, t, x_ref, diag=np.full(N, 9.0))
+        assert quad[0] == pytest.approx(o_q, rel=1e-9) and logdet2[0] == pytest.approx(o_ld2, rel=1e-11)
+        # stored factor: compute + log_likelihood + dot_tril + apply_inverse
+        gp = g.GaussianProcess(k, t=t, diag=np.full(N, 9.0), solver=solver)
+        ogp = oracle.OracleGP(scan, t, diag=np.full(N, 9.0))
+        assert gp.log_likelihood(x_ref) == pytest.approx(ogp.log_likelihood(x_ref), rel=1e-9)
+        assert np.max(np.abs(gp.dot_tril(nrm) - ogp.dot_tril(nrm))) <= 1e-9 * np.max(np.abs(x_ref))
+        ai, oai = gp.apply_inverse(x_ref), ogp.apply_inverse(x_ref)
+        assert np.max(np.abs(ai - oai)) <= 1e-7 * np.max(np.abs(oai))
+    too_many = list(solar_kernel.term.terms) * 3
+    with pytest.raises(ValueError):
+        KernelBatch([g.StellarOscillatorKernel(terms=too_many, delta=solar_kernel.delta)])
