@@ -33,8 +33,22 @@ def _geometry(kb, t, lengths):
     return Geometry.ragged(lengths)
 
 
+class PendingLogLikelihood:
+    """Result of ``log_likelihood(..., wait=False)``: the copies and the kernel are queued; ``result()``
+    blocks until THIS call has completed (not later ones) and returns what ``log_likelihood`` returns."""
+
+    def __init__(self, solver, ticket, finish):
+        self._solver, self._ticket, self._finish, self._value = solver, ticket, finish, None
+
+    def result(self):
+        if self._finish is not None:
+            self._solver.wait(self._ticket)
+            self._value, self._finish = self._finish(), None
+        return self._value
+
+
 def log_likelihood(kernels, t, y, diag=None, lengths=None, mean=0.0, quiet=True, solver=None,
-                   return_parts=False, flags=0):
+                   return_parts=False, flags=0, wait=True):
     """log-likelihood of B light curves under B kernels.
 
     ``t``: ``[N]`` (one cadence shared by all units), ``[B, N]``, or a flat concatenation
@@ -50,18 +64,27 @@ def log_likelihood(kernels, t, y, diag=None, lengths=None, mean=0.0, quiet=True,
         y = np.ascontiguousarray(y, dtype=np.float64)
         if np.any(mean != 0.0):
             y = y - mean
-    logdet, quad, status = solver.loglike(kb, geom, t, y, diag, flags=flags)
-    N = np.diff(geom.n_off)
-    ll = -0.5 * (quad + logdet + N * _LOG_2PI)
-    bad = status != 0
-    if np.any(bad):
-        if not quiet:
-            b = int(np.flatnonzero(bad)[0])
-            raise LinAlgError(f"unit {b}: failed to factorize, d[{status[b] - 1}] <= 0")
-        ll = np.where(bad, -np.inf, ll)
-    if return_parts:
-        return ll, logdet, quad, status
-    return ll
+    from .solver import FLAG_ASYNC
+    logdet, quad, status = solver.loglike(kb, geom, t, y, diag, flags=flags | (0 if wait else FLAG_ASYNC))
+
+    def finish():
+        N = np.diff(geom.n_off)
+        ll = -0.5 * (quad + logdet + N * _LOG_2PI)
+        bad = status != 0
+        if np.any(bad):
+            if not quiet:
+                b = int(np.flatnonzero(bad)[0])
+                raise LinAlgError(f"unit {b}: failed to factorize, d[{status[b] - 1}] <= 0")
+            ll = np.where(bad, -np.inf, ll)
+        if return_parts:
+            return ll, logdet, quad, status
+        return ll
+
+    if not wait:
+        # (``wait=False``: y / t must stay alive and unchanged until result(); the next call's copies
+        # and kernels can be queued behind this one -- bench.py's end-to-end loop)
+        return PendingLogLikelihood(solver, solver.ticket(), finish)
+    return finish()
 
 
 def log_likelihood_gradient(S0, w0, Q, delta, t, y, diag=None, wrt=('S0', 'w0', 'Q'), rel_step=2e-3,

@@ -52,6 +52,8 @@ cudaError_t launch_cond_mean(int64_t N, const double *t, int64_t M, const double
 
 namespace {
 
+constexpr int N_COUNTERS = 4096;
+
 enum Slot {
     S_NOFF, S_TOFF, S_JOFF, S_WOFF, S_ORDER, S_COUNTER, S_T, S_Y, S_DIAG, S_COEF, S_DDIAG,
     S_OUT, S_OUTW, S_LOGDET, S_QUAD, S_STATUS, S_OMEGA, S_DELTA, S_W, S_SCRATCH,
@@ -96,6 +98,11 @@ struct gf_context {
     bool timed = false;
     std::string err;
     gf::FftPlan *fft = nullptr;
+    int *counters = nullptr;             // ring of zeroed work-queue heads (device)
+    int counter_next = 0;
+    cudaEvent_t ticket_ev[8] = {};       // completion tickets of GF_FLAG_ASYNC calls (gf_ticket / gf_wait)
+    int64_t ticket_no[8] = {};
+    int64_t tickets = 0;
     Pair buf[N_SLOTS];
 };
 
@@ -338,11 +345,21 @@ int run_scan(gf_handle h, int mode, int64_t B, const int64_t *n_off, const int64
     GF_CUDA(h, stage_in(h, S_ORDER, (const int32_t *)g.order.data(), (size_t)B, &order_dev));
     A.order = order_dev;
     {
-        void *cnt = nullptr;
-        GF_CUDA(h, reserve(h, S_COUNTER, sizeof(int), &cnt));
-        A.counter = (int *)cnt;
-        GF_CUDA(h, cudaMemsetAsync(A.counter, 0, sizeof(int), h->stream));
+        // Work-queue head of this launch: the next of a ring of pre-zeroed counters.  (Not a memset per
+        // launch: a memset is a copy-engine operation, and behind a bulk H2D copy on that engine it
+        // would hold the kernel back for the whole transfer -- the reason the H2D copy of the next
+        // light curves did not overlap the running scan in round 1.)
+        if (h->counter_next == N_COUNTERS) {
+            GF_CUDA(h, cudaMemsetAsync(h->counters, 0, N_COUNTERS * sizeof(int), h->stream));
+            h->counter_next = 0;
+        }
+        A.counter = h->counters + h->counter_next++;
     }
+    // (the small, usually pageable arrays first: a pageable copy blocks the host until everything queued
+    // before it on the copy-in stream has been copied -- behind the bulk arrays that would be their whole
+    // transfer time)
+    GF_CUDA(h, stage_in(h, S_COEF, coef, (size_t)g.total_j * 4, &A.coef));
+    GF_CUDA(h, stage_in(h, S_DDIAG, ddiag, (size_t)B, &A.ddiag));
     GF_CUDA(h, stage_in(h, S_T, t, (size_t)t_len, &A.t));
     const bool shared_y = (flags & GF_FLAG_SHARED_Y) != 0;
     if (shared_y && mode != gf::MODE_LOGLIKE) return fail(h, GF_E_ARG, "GF_FLAG_SHARED_Y: log-likelihood only");
@@ -350,8 +367,6 @@ int run_scan(gf_handle h, int mode, int64_t B, const int64_t *n_off, const int64
     const size_t y_len = shared_y ? (size_t)t_len : (size_t)g.total_n;
     GF_CUDA(h, stage_in(h, S_Y, y, y_len, &A.y));
     GF_CUDA(h, stage_in(h, S_DIAG, diag, y_len, &A.diag));
-    GF_CUDA(h, stage_in(h, S_COEF, coef, (size_t)g.total_j * 4, &A.coef));
-    GF_CUDA(h, stage_in(h, S_DDIAG, ddiag, (size_t)B, &A.ddiag));
     A.seed = seed;
     A.seq0 = seq0;
 
@@ -435,6 +450,8 @@ int gf_create(int device, gf_handle *out)
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&h->counters, N_COUNTERS * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(h->counters, 0, N_COUNTERS * sizeof(int));
     if (e != cudaSuccess) { gf_destroy(h); return (int)e; }
     *out = h;
     return GF_OK;
@@ -451,8 +468,10 @@ int gf_destroy(gf_handle h)
             if (b.ev) cudaEventDestroy(b.ev);
         }
     for (cudaEvent_t ev : {h->ev0, h->ev1, h->ev_in, h->ev_k, h->ev_ext}) if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : h->ticket_ev) if (ev) cudaEventDestroy(ev);
     for (cudaStream_t st : {h->stream, h->s_in, h->s_out}) if (st) cudaStreamDestroy(st);
     if (h->fft) gf::delete_fft_plan(h->fft);
+    if (h->counters) cudaFree(h->counters);
     delete h;
     return GF_OK;
 }
@@ -473,6 +492,32 @@ int gf_wait_stream(gf_handle h, void *producer)
     Guard guard(h->device);
     GF_CUDA(h, cudaEventRecord(h->ev_ext, (cudaStream_t)producer));
     GF_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_ext, 0));
+    return GF_OK;
+}
+
+int64_t gf_ticket(gf_handle h)
+{
+    if (!h) return GF_E_ARG;
+    Guard guard(h->device);
+    const int64_t no = ++h->tickets;
+    const int k = (int)(no & 7);
+    if (!h->ticket_ev[k]) GF_CUDA(h, cudaEventCreateWithFlags(&h->ticket_ev[k], cudaEventDisableTiming));
+    // everything issued so far: the kernels (compute stream), then the copies back (copy-out stream)
+    GF_CUDA(h, cudaEventRecord(h->ev_ext, h->stream));
+    GF_CUDA(h, cudaStreamWaitEvent(h->s_out, h->ev_ext, 0));
+    GF_CUDA(h, cudaEventRecord(h->ticket_ev[k], h->s_out));
+    h->ticket_no[k] = no;
+    return no;
+}
+
+int gf_wait(gf_handle h, int64_t ticket)
+{
+    if (!h) return GF_E_ARG;
+    if (ticket <= 0 || ticket > h->tickets) return fail(h, GF_E_ARG, "unknown ticket");
+    Guard guard(h->device);
+    const int k = (int)(ticket & 7);
+    // a ticket older than the ring has been overwritten by a later one: waiting for that is sufficient
+    GF_CUDA(h, cudaEventSynchronize(h->ticket_ev[k]));
     return GF_OK;
 }
 

@@ -68,6 +68,8 @@ _SIGNATURES = {
     "gf_synchronize": (ctypes.c_int, [ctypes.c_void_p]),
     "gf_last_error": (ctypes.c_char_p, [ctypes.c_void_p]),
     "gf_stream": (ctypes.c_void_p, [ctypes.c_void_p]),
+    "gf_ticket": (ctypes.c_int64, [ctypes.c_void_p]),
+    "gf_wait": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64]),
     "gf_wait_stream": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "gf_stream_wait": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "gf_device_info": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int),
@@ -285,6 +287,17 @@ class Solver:
 
     def synchronize(self):
         self._check(self._lib.gf_synchronize(self._h))
+
+    def ticket(self):
+        """Mark "everything issued so far, copies back to host buffers included" (FLAG_ASYNC calls)."""
+        t = int(self._lib.gf_ticket(self._h))
+        if t <= 0:
+            self._check(t)
+        return t
+
+    def wait(self, ticket):
+        """Block until the work marked by ``ticket`` has completed (later calls may still be running)."""
+        self._check(self._lib.gf_wait(self._h, int(ticket)))
 
     # Device buffers are touched on the handle's compute stream only (include/gadfly_b200.h,
     # "Streams"): whatever torch stream produced a CUDA tensor we are handed must be ordered

@@ -86,6 +86,14 @@ void *gf_stream(gf_handle h);
 /* make the compute stream wait for everything enqueued so far on `producer` (a cudaStream_t;
  * NULL = the legacy default stream): call it before passing device buffers that `producer` wrote */
 int gf_wait_stream(gf_handle h, void *producer);
+/* Completion tickets for GF_FLAG_ASYNC calls with HOST outputs: gf_ticket() marks "everything issued on
+ * this handle so far, including the copies back to host buffers" and returns a ticket (> 0);
+ * gf_wait(h, ticket) blocks the host until that point -- and not until later calls -- has completed, so
+ * that a caller can keep the next call's copies and kernels queued behind the running ones (a copy
+ * submitted while a scan kernel runs only overlaps it if it was already queued when the kernel
+ * started: DESIGN.md section 3).  Up to 8 tickets may be outstanding. */
+int64_t gf_ticket(gf_handle h);
+int gf_wait(gf_handle h, int64_t ticket);
 /* make `consumer` (a cudaStream_t) wait for everything enqueued so far on the compute stream:
  * call it before `consumer` reads device outputs of a GF_FLAG_ASYNC call */
 int gf_stream_wait(gf_handle h, void *consumer);

@@ -526,3 +526,16 @@ def test_log_likelihood_gradient_vs_definition(solver):
     g_w0 = batch.log_likelihood_gradient(gd["S0"], gd["w0"], gd["Q"], float(gd["delta"]), gd["t"], gd["y"],
                                          diag=gd["diag"], wrt=("w0",), solver=solver)
     np.testing.assert_allclose(g_w0[0], grad[1], rtol=1e-12)
+
+
+def test_async_calls_with_tickets(solver, solar_kernel):
+    """``log_likelihood(wait=False)``: several calls queued back to back on one handle (host buffers,
+    ping-pong staging), each result read through its own completion ticket, equal to the blocking call."""
+    rng = np.random.default_rng(3)
+    N, B = 3000, 5
+    t = np.arange(N) * 6e-5
+    ys = [rng.standard_normal((B, N)) * 280.0 for _ in range(4)]
+    ref = [batch.log_likelihood([solar_kernel] * B, t, y, solver=solver) for y in ys]
+    pend = [batch.log_likelihood([solar_kernel] * B, t, y, solver=solver, wait=False) for y in ys]
+    for p, r in zip(reversed(pend), reversed(ref)):
+        np.testing.assert_array_equal(p.result(), r)
