@@ -539,3 +539,42 @@ def test_async_calls_with_tickets(solver, solar_kernel):
     pend = [batch.log_likelihood([solar_kernel] * B, t, y, solver=solver, wait=False) for y in ys]
     for p, r in zip(reversed(pend), reversed(ref)):
         np.testing.assert_array_equal(p.result(), r)
+
+
+def test_fit_with_device_gradients(solver):
+    """What the gradients are for (the reference fits its solar kernel with celerite2.jax + BFGS,
+    notebooks/virgo_lc.ipynb:48): maximise log L over ln(S0, w0, Q) of a 4-term kernel with scipy's
+    L-BFGS-B, value and gradient from ``batch.log_likelihood_gradient`` (one batched launch per
+    evaluation).  Starting 20-30 % off, the fit climbs to within a few units of the log-likelihood at
+    the parameters the data were drawn from (or above it)."""
+    from scipy.optimize import minimize
+    rng = np.random.default_rng(5)
+    S0 = np.array([600.0, 8.0, 2.0e-3, 3.0e-3])
+    w0 = np.array([9.0, 150.0, 17500.0, 19800.0])
+    Q = np.array([0.6, 0.7, 300.0, 450.0])
+    delta, N = 2e-4, 3000
+    t = np.arange(N) * 2.5e-4
+    diag = np.full(N, 9.0)
+    truth = g.StellarOscillatorKernel(terms=[g.SHOTerm(S0=a, w0=b, Q=c) for a, b, c in zip(S0, w0, Q)], delta=delta)
+    y, st = batch.sample([truth], t, diag, seed=77, solver=solver, subtract_mean=False)
+    y = y[0] + 3.0 * rng.standard_normal(N)
+    assert st[0] == 0
+    ll_true = batch.log_likelihood([truth], t, y[None, :], diag, solver=solver)[0]
+    x_true = np.log(np.concatenate([S0, w0, Q]))
+    x0 = x_true + np.concatenate([0.3 * rng.uniform(-1, 1, 4), [0.2, -0.2, 2e-3, -2e-3], 0.3 * rng.uniform(-1, 1, 4)])
+    x0[8] = max(x0[8], np.log(0.55))      # granulation terms stay underdamped (Q > 0.5)
+    x0[9] = max(x0[9], np.log(0.55))
+    calls = []
+
+    def objective(x):
+        p = np.exp(x)
+        grad, ll = batch.log_likelihood_gradient(p[:4], p[4:8], p[8:], delta, t, y, diag=diag, solver=solver,
+                                                 return_value=True)
+        calls.append(ll)
+        return -ll, -grad.ravel()
+
+    bounds = [(None, None)] * 8 + [(np.log(0.51), None)] * 4
+    res = minimize(objective, x0, jac=True, method="L-BFGS-B", bounds=bounds, options=dict(maxiter=60))
+    assert calls[0] < ll_true - 20.0            # the start is clearly worse than the truth
+    assert -res.fun > ll_true - 5.0             # the fit is as good as the truth (12 parameters)
+    assert np.all(np.abs(res.x[4:8] - x_true[4:8]) < np.array([0.5, 0.5, 2e-3, 2e-3]))   # frequencies recovered

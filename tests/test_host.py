@@ -299,3 +299,20 @@ def test_for_star_matches_independent_evaluation():
             sl = slice(hpb.j_off[b], hpb.j_off[b + 1])
             for key, arr in (("S0", hpb.S0), ("w0", hpb.w0), ("Q", hpb.Q)):
                 np.testing.assert_allclose(arr[sl], st[key], rtol=1e-12, err_msg=f"batched {name} {key}")
+
+
+def test_bin_ranges_match_host_binning():
+    """The index ranges handed to the device binning kernel are scipy.stats.binned_statistic's bins
+    (what ``bin_power_spectrum`` uses on the host): every point in exactly one bin, the last edge
+    closed on the right, points on an inner edge in the bin to its right."""
+    from gadfly_b200 import psd as P
+    rng = np.random.default_rng(1)
+    for axis in (np.log10(np.fft.rfftfreq(5000, 6e-5)[1:]), np.sort(rng.uniform(0, 10, 777)),
+                 np.linspace(0.0, 1.0, 101)):
+        for bins in (1, 7, 15, 100):
+            edges, lo, cnt = P.bin_ranges(axis, bins)
+            assert cnt.sum() == len(axis) and np.all(lo[1:] == lo[:-1] + cnt[:-1]) and lo[0] == 0
+            which = np.searchsorted(edges, axis, side='right') - 1
+            which[axis == edges[-1]] = bins - 1
+            for k in range(bins):
+                assert np.array_equal(np.flatnonzero(which == k), np.arange(lo[k], lo[k] + cnt[k]))
