@@ -48,7 +48,7 @@ def _alpha(bandpass, alpha, T):
     filt = Filter(bandpass)
     if filt.mean_wavelength is None:     # flat bandpass: both ratios of Morris+ (2020) Eqn 11 are 1
         return np.ones_like(T), None
-    return np.array([scale.amplitude_with_wavelength(filt, t) for t in T]), filt.mean_wavelength
+    return scale.amplitude_with_wavelength_many(filt, T), filt.mean_wavelength
 
 
 def for_stars(mass, radius, temperature, luminosity, bandpass='SOHO VIRGO', alpha=None):

@@ -162,6 +162,36 @@ def _trapz(y, x):
     return float(np.sum(0.5 * (y[1:] + y[:-1]) * np.diff(x)))
 
 
+def amplitude_with_wavelength_many(filter, temperatures, n_wavelengths=10_000, chunk=256):
+    """:func:`amplitude_with_wavelength` for an array of temperatures at once (the batched feeder's
+    non-flat bandpasses): the same quadrature, broadcast over ``[stars, wavelengths]`` in chunks."""
+    T = np.atleast_1d(np.asarray(temperatures, dtype=np.float64))
+    wl = np.logspace(-1.5, 1.5, n_wavelengths)  # micron
+    if isinstance(filter, str):
+        if filter.upper() == 'SOHO VIRGO':
+            return np.ones_like(T)
+        raise ValueError(
+            f"filter must be 'SOHO VIRGO' or an object with wavelength/transmittance "
+            f"arrays (tynt's filter tables are not bundled), but got: {filter}")
+    f_wl = np.asarray(to_value(filter.wavelength, u.um), dtype=float)
+    f_tr = np.asarray(filter.transmittance, dtype=float)
+    filt1 = np.interp(wl, f_wl, f_tr, left=0, right=0)
+    dx = np.diff(wl)
+
+    def trapz(y):       # same summation as _trapz, along the wavelength axis
+        return np.sum(0.5 * (y[:, 1:] + y[:, :-1]) * dx, axis=1)
+
+    out = np.empty_like(T)
+    for lo in range(0, len(T), chunk):
+        Tc = T[lo:lo + chunk, None]
+        I_nu = _planck_nu(wl[None, :], Tc)
+        dI_dT = (_planck_nu(wl[None, :], Tc + 10.0) - _planck_nu(wl[None, :], Tc - 10.0)) / 20.0
+        ratio_0 = trapz(dI_dT * wl * filt1) / trapz(dI_dT * wl)
+        ratio_1 = trapz(I_nu * wl) / trapz(I_nu * wl * filt1)
+        out[lo:lo + chunk] = ratio_0 * ratio_1
+    return out
+
+
 def amplitude_with_wavelength(filter, temperature, n_wavelengths=10_000, **kwargs):
     """Amplitude of intensity features in a bandpass relative to SOHO VIRGO/PMO6
     (bolometric), Morris et al. (2020) Eqn 11 (reference gadfly/scale.py:635-729).

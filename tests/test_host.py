@@ -247,6 +247,16 @@ def test_batched_feeder_matches_per_star():
     gran = slice(0, 5)
     np.testing.assert_allclose(kb2.base[gran, 0], 2.0 * kb.base[gran, 0], rtol=1e-13)
 
+    # a tabulated (non-flat) bandpass: the batched amplitude ratio equals the per-star quadrature
+    class Band:
+        wavelength = np.linspace(0.4, 0.9, 200) * u.um
+        transmittance = np.exp(-0.5 * ((np.linspace(0.4, 0.9, 200) - 0.65) / 0.1) ** 2)
+        mean_wavelength = 0.65 * u.um
+    many = scale.amplitude_with_wavelength_many(Band, T)
+    one = np.array([scale.amplitude_with_wavelength(Band, t) for t in T])
+    np.testing.assert_allclose(many, one, rtol=1e-14)
+    assert np.array_equal(scale.amplitude_with_wavelength_many('SOHO VIRGO', T), np.ones(len(T)))
+
 
 def test_get_value_matches_oracle_and_defining_integral(solar_kernel):
     """Term.get_value / TermConvolution.get_value (celerite2 API used by the predictive variance):
