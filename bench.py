@@ -397,10 +397,10 @@ def run_b200(args):
             # stream); the log-likelihood kernel then runs beside the D2H copy of x (copy-out stream).
             # Nothing blocks the host here: the step's result is read one step later (result() waits
             # for THAT step's ticket), so the next step's copies and kernels are queued behind the
-            # running ones.  Measured (tools/e2e_probe.py): the D2H copy hides completely behind the
-            # log-likelihood kernel; the H2D copy of y does NOT start while a scan kernel of this
-            # library runs (a minimal CUDA program with the same launch shape overlaps, tools/
-            # overlap_probe.cu: cause not found), so it costs its 22 ms = 1.1 % per step.
+            # running ones.  (The small outputs -- log det, status: ordinary numpy arrays -- reach the
+            # host through the handle's pinned ring; copied straight into pageable memory they held
+            # the host until the kernel had finished, which is what kept H2D(y) from overlapping in
+            # round 1 and early round 2: tools/overlap_probe2.cu, overlap_probe3.py, e2e_probe.py.)
             solver.sample(kb, geom, t_np, seed=2000 + i, seq0=rank * B, out=x_np, flags=S.FLAG_ASYNC)
             return batch.log_likelihood(kb, t_np, y_np, solver=solver, wait=False)
 

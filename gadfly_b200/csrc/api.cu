@@ -12,6 +12,7 @@
 #include <new>
 #include <numeric>
 #include <string>
+#include <deque>
 #include <vector>
 
 namespace gf {
@@ -80,6 +81,15 @@ struct Pair {
     Buf b[2];
 };
 
+struct Deferred {
+    void *user;            // pageable destination
+    const char *pinned;    // where the copy-out stream puts it
+    size_t bytes, ring_end;
+    int64_t seq;
+};
+constexpr size_t BOUNCE_BYTES = 8u << 20;      // ring of pinned memory per handle
+constexpr size_t BOUNCE_MAX = 1u << 20;        // larger pageable outputs are copied directly (host waits)
+
 }  // namespace
 
 struct gf_context {
@@ -102,7 +112,16 @@ struct gf_context {
     int counter_next = 0;
     cudaEvent_t ticket_ev[8] = {};       // completion tickets of GF_FLAG_ASYNC calls (gf_ticket / gf_wait)
     int64_t ticket_no[8] = {};
+    int64_t ticket_seq[8] = {};          // last deferred output the ticket covers
     int64_t tickets = 0;
+    // Small outputs into PAGEABLE host memory: a device-to-host cudaMemcpyAsync into pageable memory
+    // returns only when the copy is done, i.e. it would hold the host until the kernel before it has
+    // finished and GF_FLAG_ASYNC would not be asynchronous at all.  They go through a ring of pinned
+    // memory instead and reach the caller's buffer in gf_synchronize / gf_wait / the next blocking call.
+    char *bounce = nullptr;
+    size_t bounce_head = 0, bounce_tail = 0;
+    std::deque<Deferred> deferred;
+    int64_t out_seq = 0;
     Pair buf[N_SLOTS];
 };
 
@@ -131,12 +150,46 @@ int fail(gf_handle h, int code, const char *what)
         if (e__ != cudaSuccess) return fail((h), (int)e__, #expr);            \
     } while (0)
 
-bool is_device_ptr(const void *p)
+enum { P_PAGEABLE = 0, P_PINNED = 1, P_DEVICE = 2 };
+int pointer_kind(const void *p)
 {
     cudaPointerAttributes a;
     cudaError_t e = cudaPointerGetAttributes(&a, p);
-    if (e != cudaSuccess) { cudaGetLastError(); return false; }
-    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+    if (e != cudaSuccess) { cudaGetLastError(); return P_PAGEABLE; }
+    if (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) return P_DEVICE;
+    return a.type == cudaMemoryTypeHost ? P_PINNED : P_PAGEABLE;
+}
+bool is_device_ptr(const void *p) { return pointer_kind(p) == P_DEVICE; }
+
+// a slice of the pinned ring (nullptr: no room, or no ring)
+char *bounce_alloc(gf_handle h, size_t bytes, size_t *ring_end)
+{
+    if (!h->bounce) return nullptr;
+    bytes = (bytes + 63) & ~(size_t)63;
+    if (h->deferred.empty()) h->bounce_head = h->bounce_tail = 0;
+    size_t off;
+    if (h->bounce_head >= h->bounce_tail) {
+        if (h->bounce_head + bytes <= BOUNCE_BYTES) off = h->bounce_head;
+        else if (bytes < h->bounce_tail) off = 0;
+        else return nullptr;
+    } else {
+        if (h->bounce_head + bytes < h->bounce_tail) off = h->bounce_head;
+        else return nullptr;
+    }
+    h->bounce_head = off + bytes;
+    *ring_end = h->bounce_head;
+    return h->bounce + off;
+}
+
+// the copy-out stream has completed every deferred output up to `upto`: hand them to the caller
+void flush_deferred(gf_handle h, int64_t upto)
+{
+    while (!h->deferred.empty() && h->deferred.front().seq <= upto) {
+        const Deferred &d = h->deferred.front();
+        std::memcpy(d.user, d.pinned, d.bytes);
+        h->bounce_tail = d.ring_end;
+        h->deferred.pop_front();
+    }
 }
 
 // A staging buffer of at least `bytes` for `slot` whose previous use is either complete or is
@@ -213,15 +266,18 @@ struct Out {
     T *dev = nullptr;
     size_t count = 0;
     bool host = false;
+    bool pageable = false;
     Buf *buf = nullptr;
 };
 
 template <typename T>
 cudaError_t stage_out(gf_handle h, int slot, T *dst, size_t count, Out<T> *o)
 {
-    o->user = dst; o->count = count; o->host = false; o->dev = dst; o->buf = nullptr;
+    o->user = dst; o->count = count; o->host = false; o->pageable = false; o->dev = dst; o->buf = nullptr;
     if (!dst || count == 0) return cudaSuccess;
-    if (is_device_ptr(dst)) return cudaSuccess;
+    const int kind = pointer_kind(dst);
+    if (kind == P_DEVICE) return cudaSuccess;
+    o->pageable = kind == P_PAGEABLE;
     cudaError_t e = acquire(h, slot, count * sizeof(T), h->stream, &o->buf);
     if (e != cudaSuccess) return e;
     o->dev = (T *)o->buf->p;
@@ -260,7 +316,15 @@ template <typename T>
 cudaError_t finish_out(gf_handle h, const Out<T> &o)
 {
     if (!o.host || !o.user || o.count == 0) return cudaSuccess;
-    cudaError_t e = cudaMemcpyAsync(o.user, o.dev, o.count * sizeof(T), cudaMemcpyDeviceToHost, h->s_out);
+    const size_t bytes = o.count * sizeof(T);
+    void *dst = o.user;
+    size_t ring_end = 0;
+    char *pinned = (o.pageable && bytes <= BOUNCE_MAX) ? bounce_alloc(h, bytes, &ring_end) : nullptr;
+    if (pinned) {
+        dst = pinned;
+        h->deferred.push_back(Deferred{o.user, pinned, bytes, ring_end, ++h->out_seq});
+    }
+    cudaError_t e = cudaMemcpyAsync(dst, o.dev, bytes, cudaMemcpyDeviceToHost, h->s_out);
     if (e != cudaSuccess) return e;
     e = cudaEventRecord(o.buf->ev, h->s_out);
     o.buf->pending = true;
@@ -274,7 +338,9 @@ cudaError_t finish_call(gf_handle h, uint32_t flags)
     if (flags & GF_FLAG_ASYNC) return cudaSuccess;
     cudaError_t e = cudaStreamSynchronize(h->stream);
     if (e != cudaSuccess) return e;
-    return cudaStreamSynchronize(h->s_out);
+    e = cudaStreamSynchronize(h->s_out);
+    if (e == cudaSuccess) flush_deferred(h, h->out_seq);
+    return e;
 }
 
 // Batch geometry shared by the scan entry points.
@@ -452,6 +518,7 @@ int gf_create(int device, gf_handle *out)
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = cudaMalloc((void **)&h->counters, N_COUNTERS * sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(h->counters, 0, N_COUNTERS * sizeof(int));
+    if (e == cudaSuccess) e = cudaHostAlloc((void **)&h->bounce, BOUNCE_BYTES, cudaHostAllocDefault);
     if (e != cudaSuccess) { gf_destroy(h); return (int)e; }
     *out = h;
     return GF_OK;
@@ -472,6 +539,8 @@ int gf_destroy(gf_handle h)
     for (cudaStream_t st : {h->stream, h->s_in, h->s_out}) if (st) cudaStreamDestroy(st);
     if (h->fft) gf::delete_fft_plan(h->fft);
     if (h->counters) cudaFree(h->counters);
+    flush_deferred(h, h->out_seq);
+    if (h->bounce) cudaFreeHost(h->bounce);
     delete h;
     return GF_OK;
 }
@@ -483,6 +552,7 @@ int gf_synchronize(gf_handle h)
     GF_CUDA(h, cudaStreamSynchronize(h->s_in));
     GF_CUDA(h, cudaStreamSynchronize(h->stream));
     GF_CUDA(h, cudaStreamSynchronize(h->s_out));
+    flush_deferred(h, h->out_seq);
     return GF_OK;
 }
 
@@ -507,6 +577,7 @@ int64_t gf_ticket(gf_handle h)
     GF_CUDA(h, cudaStreamWaitEvent(h->s_out, h->ev_ext, 0));
     GF_CUDA(h, cudaEventRecord(h->ticket_ev[k], h->s_out));
     h->ticket_no[k] = no;
+    h->ticket_seq[k] = h->out_seq;
     return no;
 }
 
@@ -518,6 +589,7 @@ int gf_wait(gf_handle h, int64_t ticket)
     const int k = (int)(ticket & 7);
     // a ticket older than the ring has been overwritten by a later one: waiting for that is sufficient
     GF_CUDA(h, cudaEventSynchronize(h->ticket_ev[k]));
+    flush_deferred(h, h->ticket_seq[k]);
     return GF_OK;
 }
 

@@ -26,7 +26,7 @@ import threading
 import numpy as np
 
 __all__ = ["Solver", "KernelBatch", "SolverUnavailable", "LinAlgError", "default_solver",
-           "library_path", "GF_MAX_J", "FLAG_ASYNC", "FLAG_REFERENCE_ORDER"]
+           "library_path", "DevicePointer", "GF_MAX_J", "FLAG_ASYNC", "FLAG_REFERENCE_ORDER"]
 
 GF_MAX_J = 176          # widest state of the register-resident scans
 GF_MAX_J_WIDE = 352     # widest state at all (slower kernel, state in L2-resident scratch)
@@ -135,10 +135,25 @@ def load_library(path=None):
 # ---------------------------------------------------------------------------------------
 # pointers: numpy arrays (host) or anything with ``data_ptr()`` (a torch CUDA/CPU tensor)
 # ---------------------------------------------------------------------------------------
+class DevicePointer:
+    """A raw device (or pinned host) address with an element count, for callers that manage memory
+    without torch (cuda-python, cupy ...).  Ordering against other streams is the caller's business
+    (``Solver.stream``, gf_wait_stream / gf_stream_wait)."""
+
+    def __init__(self, address, count, dtype=np.float64):
+        self.address, self.count, self.dtype = int(address), int(count), dtype
+
+
 def _addr(x, dtype=np.float64, count=None, name="array"):
     """(address, keepalive) of a contiguous float64/int32 buffer on host or device."""
     if x is None:
         return None, None
+    if isinstance(x, DevicePointer):
+        if x.dtype != dtype:
+            raise TypeError(f"{name}: pointer to {x.dtype}, need {dtype}")
+        if count is not None and x.count < count:
+            raise ValueError(f"{name}: {x.count} elements, need {count}")
+        return x.address, x
     if hasattr(x, "data_ptr"):  # torch tensor
         import torch
         want = {np.float64: torch.float64, np.int32: torch.int32, np.int64: torch.int64}[dtype]
@@ -157,7 +172,7 @@ def _out(x, shape, dtype=np.float64):
     """An output buffer: the caller's (tensor or ndarray, written in place) or a new ndarray."""
     if x is None:
         x = np.empty(shape, dtype=dtype)
-    elif not hasattr(x, "data_ptr"):
+    elif not hasattr(x, "data_ptr") and not isinstance(x, DevicePointer):
         if not (isinstance(x, np.ndarray) and x.dtype == dtype and x.flags.c_contiguous):
             raise TypeError("output must be a C-contiguous ndarray of the right dtype")
     addr, keep = _addr(x, dtype, int(np.prod(shape)))
@@ -263,6 +278,9 @@ class Solver:
                 f"gf_create(device={device}) failed with code {rc}: no usable CUDA device. "
                 f"gadfly_b200 has no CPU fallback.")
         self._h = h
+        self._calls = 0
+        self._inflight = []
+        self._ticket_call = {}
         self.device = int(device)
 
     def close(self):
@@ -287,17 +305,23 @@ class Solver:
 
     def synchronize(self):
         self._check(self._lib.gf_synchronize(self._h))
+        self._inflight.clear()
 
     def ticket(self):
         """Mark "everything issued so far, copies back to host buffers included" (FLAG_ASYNC calls)."""
         t = int(self._lib.gf_ticket(self._h))
         if t <= 0:
             self._check(t)
+        self._ticket_call[t] = self._calls
         return t
 
     def wait(self, ticket):
         """Block until the work marked by ``ticket`` has completed (later calls may still be running)."""
         self._check(self._lib.gf_wait(self._h, int(ticket)))
+        upto = self._ticket_call.get(int(ticket))
+        if upto is not None:
+            self._inflight = [(c, a) for c, a in self._inflight if c > upto]
+            self._ticket_call = {k: v for k, v in self._ticket_call.items() if k > int(ticket)}
 
     # Device buffers are touched on the handle's compute stream only (include/gadfly_b200.h,
     # "Streams"): whatever torch stream produced a CUDA tensor we are handed must be ordered
@@ -315,6 +339,16 @@ class Solver:
                 self._check(self._lib.gf_wait_stream(self._h, ctypes.c_void_p(cur)))
 
     def _order_after(self, flags, *xs):
+        # Host outputs of a FLAG_ASYNC call are written when the work completes (pageable ones in
+        # gf_synchronize / gf_wait, from the library's pinned ring): keep them alive until then,
+        # whatever the caller does with the returned arrays.
+        if flags & FLAG_ASYNC:
+            self._calls += 1
+            host = [x for x in xs if isinstance(x, np.ndarray)]
+            if host:
+                self._inflight.append((self._calls, host))
+        else:
+            self._inflight.clear()
         ts = self._cuda_tensors(xs)
         if ts and (flags & FLAG_ASYNC):
             import torch

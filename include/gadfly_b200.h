@@ -68,7 +68,14 @@ enum {
 #define GF_MAX_J_WIDE 352
 
 /* flags */
-#define GF_FLAG_ASYNC 1u          /* do not synchronise before returning */
+#define GF_FLAG_ASYNC 1u          /* do not synchronise before returning: host outputs are valid (and
+                                      their buffers must stay alive) until gf_synchronize / gf_wait /
+                                      the next blocking call on the handle.  Pinned host outputs are
+                                      written by the copy-out stream; PAGEABLE ones up to 1 MB each go
+                                      through a pinned ring inside the handle and are delivered by those
+                                      three calls (a device-to-host copy into pageable memory would hold
+                                      the host until the kernel before it has finished); a larger
+                                      pageable output is copied directly, i.e. the call blocks */
 #define GF_FLAG_REFERENCE_ORDER 2u /* use the simple reference-order scan kernel (validation) */
 #define GF_FLAG_WIDE_KERNEL 8u     /* do not take the one-warp-per-sequence path for narrow batches
                                       (all J <= 32); validation of that path against the wide kernel */
@@ -89,9 +96,8 @@ int gf_wait_stream(gf_handle h, void *producer);
 /* Completion tickets for GF_FLAG_ASYNC calls with HOST outputs: gf_ticket() marks "everything issued on
  * this handle so far, including the copies back to host buffers" and returns a ticket (> 0);
  * gf_wait(h, ticket) blocks the host until that point -- and not until later calls -- has completed, so
- * that a caller can keep the next call's copies and kernels queued behind the running ones (a copy
- * submitted while a scan kernel runs only overlaps it if it was already queued when the kernel
- * started: DESIGN.md section 3).  Up to 8 tickets may be outstanding. */
+ * that a caller can keep the next call's copies and kernels queued behind the running ones.
+ * Up to 8 tickets may be outstanding. */
 int64_t gf_ticket(gf_handle h);
 int gf_wait(gf_handle h, int64_t ticket);
 /* make `consumer` (a cudaStream_t) wait for everything enqueued so far on the compute stream:

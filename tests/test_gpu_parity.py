@@ -541,6 +541,37 @@ def test_async_calls_with_tickets(solver, solar_kernel):
         np.testing.assert_array_equal(p.result(), r)
 
 
+def test_async_call_does_not_wait_for_pageable_outputs(solver, solar_kernel):
+    """GF_FLAG_ASYNC with ordinary (pageable) numpy outputs: the call returns while its kernel is
+    still running -- a direct device-to-host copy into pageable memory would block until the kernel
+    has finished -- and the outputs are delivered by ``wait`` / ``synchronize`` through the handle's
+    pinned ring, equal to the blocking call's, also when the caller drops the returned arrays."""
+    import time
+    N, B = 60000, 148
+    t = np.arange(N) * 6e-5
+    kb = KernelBatch([solar_kernel] * B)
+    geom = Geometry.shared_t(B, N)
+    import torch
+    x_dev = torch.empty(B * N, dtype=torch.float64, device="cuda")
+    _, ld_ref, st_ref = solver.sample(kb, geom, t, seed=9, out=x_dev)
+    t0 = time.perf_counter()
+    solver.sample(kb, geom, t, seed=9, out=x_dev)
+    blocking = time.perf_counter() - t0
+    assert blocking > 0.02                                   # ~60 ms of kernel
+    t0 = time.perf_counter()
+    _, ld, st = solver.sample(kb, geom, t, seed=9, out=x_dev, flags=S.FLAG_ASYNC)
+    issued = time.perf_counter() - t0
+    solver.sample(kb, geom, t, seed=10, out=x_dev, flags=S.FLAG_ASYNC)       # returned arrays dropped
+    tk = solver.ticket()
+    _, ld3, st3 = solver.sample(kb, geom, t, seed=11, out=x_dev, flags=S.FLAG_ASYNC)
+    assert issued < 0.5 * blocking, (issued, blocking)
+    solver.wait(tk)
+    np.testing.assert_array_equal(ld, ld_ref)
+    np.testing.assert_array_equal(st, st_ref)
+    solver.synchronize()
+    np.testing.assert_array_equal(ld3, ld_ref)               # same kernel, other draws: same log det
+
+
 def test_fit_with_device_gradients(solver):
     """What the gradients are for (the reference fits its solar kernel with celerite2.jax + BFGS,
     notebooks/virgo_lc.ipynb:48): maximise log L over ln(S0, w0, Q) of a 4-term kernel with scipy's
