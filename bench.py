@@ -245,7 +245,9 @@ def leg_cfg5(args, solver, dev, rank, world, peak):
     import torch
     from gadfly_b200 import batch, solver as S, workloads
     n_stars, F, chunk = args.psd_stars, 1000000, 256
-    kb_all, feeder_s = workloads.kepler_like_batch(n_stars, 4)
+    _, host_feeder_s = workloads.kepler_like_batch(n_stars, 4)            # host feeder, for the record
+    workloads.kepler_like_batch(8, 4, solver=solver)                       # warm-up of the device feeder
+    kb_all, feeder_s = workloads.kepler_like_batch(n_stars, 4, solver=solver)
     nterm = np.diff(kb_all.j_off).astype(np.float64)
     bounds = batch.shard_bounds(nterm, world)
     lo, hi = int(bounds[rank]), int(bounds[rank + 1])
@@ -294,7 +296,7 @@ def leg_cfg5(args, solver, dev, rank, world, peak):
                 gather=dict(collective="all_gather_into_tensor (NCCL)" if world > 1 else "none (1 rank)",
                             in_timed_region=True, payload="per-star sum over the bins (rows stay sharded)",
                             bytes_per_rank=int((hi - lo) * 8)),
-                max_rel_vs_closed_form=rel, host_feeder_s=feeder_s)
+                max_rel_vs_closed_form=rel, host_feeder_s=host_feeder_s, device_feeder_s=feeder_s)
 
 # ---- the B200 arm -------------------------------------------------------------------------
 def run_b200(args):

@@ -7,6 +7,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -43,6 +44,14 @@ FftPlan *new_fft_plan();
 void delete_fft_plan(FftPlan *fp);
 cudaError_t launch_obs_power(FftPlan *fp, int64_t B, int64_t N, const double *flux, double d, int include_zero,
                              double2 *spec, double *power, cudaStream_t stream);
+int feed_max_terms();
+cudaError_t launch_feed_hyper(const FeedArgs &A, double *sho_all, unsigned char *keep_all, int32_t *count,
+                              cudaStream_t stream);
+cudaError_t launch_feed_coef(const FeedArgs &A, const double *sho_all, const unsigned char *keep_all,
+                             const int64_t *j_off, double *sho, double *coef, double *base, double *ddiag,
+                             cudaStream_t stream);
+cudaError_t launch_bandpass(int64_t B, const double *T, int64_t n_wl, const double *wl, const double *filt,
+                            double *out, cudaStream_t stream);
 cudaError_t launch_bin_power(int64_t B, int64_t F, int64_t nb, const int64_t *lo, const int64_t *cnt,
                              const double *x, const double *power, double constant, double *stat,
                              double *err, cudaStream_t stream);
@@ -62,7 +71,10 @@ enum Slot {
     S_MD, S_MW, S_MZ, S_MT, S_MDIAG, S_MCOEF, S_MDDIAG, S_VNOFF, S_VTOFF, S_VJOFF, S_VWOFF, S_VDOFF, S_VCOEF,
     S_MY, S_MOUT, S_MQUAD,
     // observed power spectrum
-    S_FLUX, S_SPEC, S_POWER, S_BLO, S_BCNT, S_BAXIS, S_BSTAT, S_BERR, S_WIDE, N_SLOTS
+    S_FLUX, S_SPEC, S_POWER, S_BLO, S_BCNT, S_BAXIS, S_BSTAT, S_BERR, S_WIDE,
+    // device feeder
+    S_FM, S_FR, S_FT, S_FL, S_FALPHA, S_FGRAN, S_FMODES, S_FSHOALL, S_FKEEP, S_FCOUNT, S_FSHO, S_FBASE, S_FDDIAG, S_FWL, S_FFILT,
+    N_SLOTS
 };
 
 // A staging buffer and the event of its last use (a kernel reading / writing it on the compute
@@ -1001,6 +1013,103 @@ int gf_bin_power_batched(gf_handle h, int64_t B, int64_t F, int64_t nb, const in
     GF_CUDA(h, end_kernel(h));
     GF_CUDA(h, finish_out(h, os));
     GF_CUDA(h, finish_out(h, oe));
+    GF_CUDA(h, finish_call(h, flags));
+    return GF_OK;
+}
+
+int gf_feed_stars(gf_handle h, int64_t B, const double *mass, const double *radius, const double *temperature,
+                  const double *luminosity, const double *alpha, double wavelength_nm, const double *delta,
+                  int64_t n_gran, const double *gran, int64_t n_modes, const double *modes, int64_t cap_terms,
+                  int64_t *j_off, double *sho, double *coef, double *base, double *ddiag, uint32_t flags)
+{
+    if (!h) return GF_E_ARG;
+    if (B < 0 || n_gran < 0 || n_modes < 0 || cap_terms < 0) return fail(h, GF_E_ARG, "negative size");
+    if (n_gran + n_modes > gf::feed_max_terms()) return fail(h, GF_E_TOO_WIDE, "more solar terms than the feeder takes");
+    if (!j_off) return fail(h, GF_E_ARG, "null j_off");
+    j_off[0] = 0;
+    if (B == 0) return GF_OK;
+    if (!mass || !radius || !temperature || !luminosity || !delta || !coef || !ddiag ||
+        (n_gran > 0 && !gran) || (n_modes > 0 && !modes))
+        return fail(h, GF_E_ARG, "null data pointer");
+    Guard guard(h);
+    const int nt = (int)(n_gran + n_modes);
+    gf::FeedArgs A;
+    std::memset(&A, 0, sizeof(A));
+    A.B = B;
+    A.n_gran = (int)n_gran;
+    A.n_modes = (int)n_modes;
+    A.wl_nm = wavelength_nm;
+    // solar normalisations of the scaling relations, in host arithmetic like the reference's
+    // (gadfly/scale.py: amplitudes Huber+ 2011, granulation Kjeldsen & Bedding 2011)
+    A.amp_huber_sun = std::pow(1.0, 0.886) / (std::pow(1.0, 1.89) * 5777.0 * std::pow(5777.0 / 5934.0, 0.8));
+    A.gran_power_sun = 1.0 / (1.0 * std::pow(5777.0, 5.5));
+    A.tau_sun = 1.0 / (1.0 * std::pow(5777.0, 3.5));
+    GF_CUDA(h, stage_in(h, S_FM, mass, (size_t)B, &A.mass));
+    GF_CUDA(h, stage_in(h, S_FR, radius, (size_t)B, &A.radius));
+    GF_CUDA(h, stage_in(h, S_FT, temperature, (size_t)B, &A.temperature));
+    GF_CUDA(h, stage_in(h, S_FL, luminosity, (size_t)B, &A.luminosity));
+    GF_CUDA(h, stage_in(h, S_FALPHA, alpha, (size_t)B, &A.alpha));
+    GF_CUDA(h, stage_in(h, S_DELTA, delta, (size_t)B, &A.delta));
+    GF_CUDA(h, stage_in(h, S_FGRAN, gran, (size_t)n_gran * 3, &A.gran));
+    GF_CUDA(h, stage_in(h, S_FMODES, modes, (size_t)n_modes * (size_t)(4 + n_gran), &A.modes));
+    void *sho_all = nullptr, *keep_all = nullptr, *count = nullptr;
+    GF_CUDA(h, reserve(h, S_FSHOALL, (size_t)B * nt * 3 * sizeof(double), &sho_all));
+    GF_CUDA(h, reserve(h, S_FKEEP, (size_t)B * nt, &keep_all));
+    GF_CUDA(h, reserve(h, S_FCOUNT, (size_t)B * sizeof(int32_t), &count));
+    GF_CUDA(h, begin_kernel(h));
+    GF_CUDA(h, gf::launch_feed_hyper(A, (double *)sho_all, (unsigned char *)keep_all, (int32_t *)count, h->stream));
+    h->launches += 1;
+    // the CSR offsets are a host array of the ABI: terms kept per star back to the host, prefix sum here
+    std::vector<int32_t> cnt((size_t)B);
+    GF_CUDA(h, cudaMemcpyAsync(cnt.data(), count, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    GF_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (int64_t b = 0; b < B; ++b) {
+        if (cnt[(size_t)b] < 0) return fail(h, GF_E_ARG, "a scaled term is overdamped (Q < 0.5): build that kernel per star");
+        j_off[b + 1] = j_off[b] + cnt[(size_t)b];
+    }
+    const int64_t total = j_off[B];
+    if (total > cap_terms) return fail(h, GF_E_ARG, "coefficient arrays too small (cap_terms)");
+    const int64_t *d_joff;
+    GF_CUDA(h, stage_in(h, S_JOFF, (const int64_t *)j_off, (size_t)B + 1, &d_joff));
+    Out<double> o_sho, o_coef, o_base, o_dd;
+    GF_CUDA(h, stage_out(h, S_FSHO, sho, (size_t)total * 3, &o_sho));
+    GF_CUDA(h, stage_out(h, S_OUT, coef, (size_t)total * 4, &o_coef));
+    GF_CUDA(h, stage_out(h, S_FBASE, base, (size_t)total * 4, &o_base));
+    GF_CUDA(h, stage_out(h, S_FDDIAG, ddiag, (size_t)B, &o_dd));
+    GF_CUDA(h, begin_kernel(h));
+    if (total > 0 || B > 0) {
+        GF_CUDA(h, gf::launch_feed_coef(A, (const double *)sho_all, (const unsigned char *)keep_all, d_joff,
+                                        o_sho.dev, o_coef.dev, o_base.dev, o_dd.dev, h->stream));
+        h->launches += 1;
+    }
+    GF_CUDA(h, end_kernel(h));
+    GF_CUDA(h, finish_out(h, o_dd));
+    GF_CUDA(h, finish_out(h, o_sho));
+    GF_CUDA(h, finish_out(h, o_coef));
+    GF_CUDA(h, finish_out(h, o_base));
+    GF_CUDA(h, finish_call(h, flags));
+    return GF_OK;
+}
+
+int gf_bandpass_amplitude(gf_handle h, int64_t B, const double *temperature, int64_t n_wl, const double *wl_um,
+                          const double *transmittance, double *out, uint32_t flags)
+{
+    if (!h) return GF_E_ARG;
+    if (B < 0 || n_wl < 0) return fail(h, GF_E_ARG, "negative size");
+    if (B == 0) return GF_OK;
+    if (!temperature || !wl_um || !transmittance || !out || n_wl < 2) return fail(h, GF_E_ARG, "null data pointer");
+    Guard guard(h);
+    const double *d_T, *d_wl, *d_f;
+    GF_CUDA(h, stage_in(h, S_FT, temperature, (size_t)B, &d_T));
+    GF_CUDA(h, stage_in(h, S_FWL, wl_um, (size_t)n_wl, &d_wl));
+    GF_CUDA(h, stage_in(h, S_FFILT, transmittance, (size_t)n_wl, &d_f));
+    Out<double> o;
+    GF_CUDA(h, stage_out(h, S_OUT, out, (size_t)B, &o));
+    GF_CUDA(h, begin_kernel(h));
+    GF_CUDA(h, gf::launch_bandpass(B, d_T, n_wl, d_wl, d_f, o.dev, h->stream));
+    h->launches += 1;
+    GF_CUDA(h, end_kernel(h));
+    GF_CUDA(h, finish_out(h, o));
     GF_CUDA(h, finish_call(h, flags));
     return GF_OK;
 }

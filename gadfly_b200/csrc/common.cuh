@@ -121,6 +121,16 @@ __device__ __forceinline__ double logdet_total(double logsum, double prod, long 
     return (logsum + log(prod)) + 0.6931471805599453 * (double)esum;
 }
 
+// (f2) device feeder: stars in, celerite coefficients out (feed.cu)
+struct FeedArgs {
+    int64_t B;
+    const double *mass, *radius, *temperature, *luminosity, *alpha, *delta;   // [B] each (alpha may be null)
+    double wl_nm, amp_huber_sun, gran_power_sun, tau_sun;
+    int n_gran, n_modes;
+    const double *gran;     // [n_gran][3]  solar (S0, w0, Q) of the granulation terms
+    const double *modes;    // [n_modes][4 + n_gran]  solar nu, Q, Gamma, unscaled height, background PSDs
+};
+
 // Upper-triangular tile enumeration: tile id -> (bi, bj), bi <= bj, row-major over bi.
 __host__ __device__ inline void tile_coords(int tile, int nb, int &bi, int &bj)
 {

@@ -18,7 +18,8 @@ from .core import _sho_psd, _solar_hyperparameter_list, Filter
 from .sun import _p_mode_fit_to_sho_hyperparams
 from .terms import TermConvolution, TermSum, SHOTerm  # noqa: F401  (documented counterparts)
 
-__all__ = ['HyperparameterBatch', 'for_stars', 'kernel_batch_from_sho', 'kernel_batch_for_stars']
+__all__ = ['HyperparameterBatch', 'for_stars', 'kernel_batch_from_sho', 'kernel_batch_for_stars',
+           'kernel_batch_for_stars_device', 'solar_tables']
 
 
 class HyperparameterBatch:
@@ -42,13 +43,75 @@ class HyperparameterBatch:
                 for s, w, q in zip(self.S0[sl], self.w0[sl], self.Q[sl])]
 
 
-def _alpha(bandpass, alpha, T):
+def _alpha(bandpass, alpha, T, solver=None):
     if alpha is not None:
         return np.broadcast_to(np.asarray(alpha, dtype=np.float64), T.shape).copy(), None
     filt = Filter(bandpass)
     if filt.mean_wavelength is None:     # flat bandpass: both ratios of Morris+ (2020) Eqn 11 are 1
         return np.ones_like(T), None
+    if solver is not None:
+        wl, tr = scale.bandpass_grid(filt)
+        return solver.bandpass_amplitude(T, wl, tr), filt.mean_wavelength
     return scale.amplitude_with_wavelength_many(filt, T), filt.mean_wavelength
+
+
+_SOLAR_TABLES = None
+
+
+def solar_tables():
+    """The star-independent half of ``for_stars`` as the two tables the device feeder takes
+    (include/gadfly_b200.h gf_feed_stars): ``gran`` [5, 3] = solar (S0, w0, Q) of the granulation
+    terms; ``modes`` [81, 4 + 5] = per solar p-mode (nu, Q, Gamma, unscaled height, background PSD
+    of each granulation term at nu); plus the mode degrees."""
+    global _SOLAR_TABLES
+    if _SOLAR_TABLES is None:
+        hp = _solar_hyperparameter_list()
+        gran = [i['hyperparameters'] for i in hp if i['metadata']['source'] == 'granulation']
+        osc = [i for i in sorted(hp, key=lambda x: x['metadata'].get('degree', -1))
+               if i['metadata']['source'] == 'oscillation']
+        p_mode_vec = np.transpose([[p['hyperparameters'].get(k) for k in ('S0', 'Q')] for p in osc]).ravel()
+        (S0_fit, solar_w0, Q_fit), ell = _p_mode_fit_to_sho_hyperparams(p_mode_vec)
+        gS0, gw0, gQ = np.transpose([[p[k] for k in ('S0', 'w0', 'Q')] for p in gran])
+        solar_nu = solar_w0 / (2 * np.pi)
+        bg = _sho_psd(2 * np.pi * solar_nu[:, None], gS0[None, :], gw0[None, :], gQ[None, :])
+        solar_Gamma = solar_nu / Q_fit / 2
+        solar_peak = _sho_psd(2 * np.pi * solar_nu, S0_fit, solar_w0, Q_fit)
+        A = 2 * np.sqrt(4 * np.pi * solar_nu * solar_peak)
+        unscaled_height = 2 * A ** 2 / (np.pi * solar_Gamma)
+        modes = np.concatenate([np.stack([solar_nu, Q_fit, solar_Gamma, unscaled_height], axis=1), bg], axis=1)
+        _SOLAR_TABLES = (np.ascontiguousarray(np.stack([gS0, gw0, gQ], axis=1)), np.ascontiguousarray(modes),
+                         ell.astype(np.int64))
+    return _SOLAR_TABLES
+
+
+def kernel_batch_for_stars_device(solver, mass, radius, temperature, luminosity, texp_s=60.0,
+                                  bandpass='SOHO VIRGO', alpha=None, return_hyperparameters=False):
+    """``kernel_batch_for_stars`` on the GPU of ``solver`` (csrc/feed.cu through gf_feed_stars):
+    scaling relations, term selection, SHO -> (a, b, c, d), exposure transform and diagonal
+    correction in two launches; the bandpass amplitude ratio, when the bandpass is not flat, in a
+    third.  Same arithmetic as the host functions of this module, device libm."""
+    from .solver import KernelBatch, GF_MAX_J_WIDE
+    M, R, T, L = (np.atleast_1d(np.asarray(x, dtype=np.float64)) for x in
+                  (mass, radius, temperature, luminosity))
+    B = len(M)
+    amp, mean_wl = _alpha(bandpass, alpha, T, solver=solver)
+    gran, modes, ell = solar_tables()
+    delta = np.broadcast_to(np.asarray(texp_s, dtype=np.float64) * 1e-6, (B,)).copy()
+    j_off, sho, coef, base, ddiag = solver.feed_stars(
+        M, R, T, L, delta, gran, modes, alpha=amp, wavelength_nm=550.0 if mean_wl is None else float(mean_wl),
+        want_sho=return_hyperparameters)
+    if B and int(np.diff(j_off).max()) * 2 > GF_MAX_J_WIDE:
+        raise ValueError(f"kernel state wider than GF_MAX_J_WIDE = {GF_MAX_J_WIDE}")
+    kb = object.__new__(KernelBatch)
+    kb.B = B
+    kb.coef = np.ascontiguousarray(coef)
+    kb.base = np.ascontiguousarray(base)
+    kb.j_off = j_off
+    kb.ddiag = ddiag
+    kb.delta = delta
+    if return_hyperparameters:
+        return kb, HyperparameterBatch(sho[:, 0], sho[:, 1], sho[:, 2], j_off)
+    return kb
 
 
 def for_stars(mass, radius, temperature, luminosity, bandpass='SOHO VIRGO', alpha=None):
@@ -171,7 +234,11 @@ def kernel_batch_from_sho(hpb, delta, eps=1e-5):
 
 
 def kernel_batch_for_stars(mass, radius, temperature, luminosity, texp_s=60.0, bandpass='SOHO VIRGO',
-                           alpha=None):
-    """Stellar parameters -> ``KernelBatch`` in one call (``texp_s``: exposure time in seconds)."""
+                           alpha=None, solver=None):
+    """Stellar parameters -> ``KernelBatch`` in one call (``texp_s``: exposure time in seconds);
+    on the host, or with ``solver=`` on that solver's GPU."""
+    if solver is not None:
+        return kernel_batch_for_stars_device(solver, mass, radius, temperature, luminosity, texp_s=texp_s,
+                                             bandpass=bandpass, alpha=alpha)
     hpb = for_stars(mass, radius, temperature, luminosity, bandpass=bandpass, alpha=alpha)
     return kernel_batch_from_sho(hpb, np.asarray(texp_s, dtype=np.float64) * 1e-6)

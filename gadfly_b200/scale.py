@@ -162,6 +162,14 @@ def _trapz(y, x):
     return float(np.sum(0.5 * (y[1:] + y[:-1]) * np.diff(x)))
 
 
+def bandpass_grid(filter, n_wavelengths=10_000):
+    """(wavelength grid [micron], transmittance on it) of the quadratures below."""
+    wl = np.logspace(-1.5, 1.5, n_wavelengths)
+    f_wl = np.asarray(to_value(filter.wavelength, u.um), dtype=float)
+    f_tr = np.asarray(filter.transmittance, dtype=float)
+    return wl, np.interp(wl, f_wl, f_tr, left=0, right=0)
+
+
 def amplitude_with_wavelength_many(filter, temperatures, n_wavelengths=10_000, chunk=256):
     """:func:`amplitude_with_wavelength` for an array of temperatures at once (the batched feeder's
     non-flat bandpasses): the same quadrature, broadcast over ``[stars, wavelengths]`` in chunks."""

@@ -103,6 +103,12 @@ _SIGNATURES = {
     "gf_bin_power_batched": (ctypes.c_int, [
         ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _i64p, _i64p, _f64p, _f64p,
         ctypes.c_double, _f64p, _f64p, ctypes.c_uint32]),
+    "gf_feed_stars": (ctypes.c_int, [
+        ctypes.c_void_p, ctypes.c_int64, _f64p, _f64p, _f64p, _f64p, _f64p, ctypes.c_double, _f64p,
+        ctypes.c_int64, _f64p, ctypes.c_int64, _f64p, ctypes.c_int64, _i64p, _f64p, _f64p, _f64p, _f64p,
+        ctypes.c_uint32]),
+    "gf_bandpass_amplitude": (ctypes.c_int, [
+        ctypes.c_void_p, ctypes.c_int64, _f64p, ctypes.c_int64, _f64p, _f64p, _f64p, ctypes.c_uint32]),
     "gf_conditional_mean": (ctypes.c_int, [
         ctypes.c_void_p, ctypes.c_int64, _f64p, ctypes.c_int64, _f64p, ctypes.c_int64, _f64p,
         _f64p, _f64p, ctypes.c_uint32]),
@@ -218,12 +224,14 @@ class KernelBatch:
             raise ValueError(f"kernel state wider than GF_MAX_J_WIDE = {GF_MAX_J_WIDE}")
 
     @staticmethod
-    def for_stars(mass, radius, temperature, luminosity, texp_s=60.0, bandpass='SOHO VIRGO', alpha=None):
+    def for_stars(mass, radius, temperature, luminosity, texp_s=60.0, bandpass='SOHO VIRGO', alpha=None,
+                  solver=None):
         """Batched ``Hyperparameters.for_star`` + kernel assembly for arrays of stars
-        (gadfly_b200/feeder.py): ~100x faster than one kernel object per star."""
+        (gadfly_b200/feeder.py): ~100x faster than one kernel object per star on the host; with
+        ``solver=`` the same arithmetic runs on that solver's GPU (csrc/feed.cu)."""
         from .feeder import kernel_batch_for_stars
         return kernel_batch_for_stars(mass, radius, temperature, luminosity, texp_s=texp_s,
-                                      bandpass=bandpass, alpha=alpha)
+                                      bandpass=bandpass, alpha=alpha, solver=solver)
 
     @property
     def J(self):
@@ -373,6 +381,49 @@ class Solver:
         fl = ctypes.c_double()
         self._check(self._lib.gf_device_info(self._h, ctypes.byref(sm), ctypes.byref(fl), int(measure)))
         return dict(sm_count=sm.value, fp64_flops=fl.value)
+
+    # -- (f2) feeder -------------------------------------------------------------------
+    def feed_stars(self, mass, radius, temperature, luminosity, delta, gran, modes, alpha=None,
+                   wavelength_nm=550.0, want_sho=True):
+        """Stellar parameters -> (j_off, sho, coef, base, ddiag) on the device (gf_feed_stars):
+        batched ``Hyperparameters.for_star`` + kernel assembly.  ``gran`` [n_gran, 3] and ``modes``
+        [n_modes, 4 + n_gran] are the star-independent solar tables (feeder.solar_tables())."""
+        M, R, T, L, D = (np.ascontiguousarray(np.atleast_1d(x), dtype=np.float64)
+                         for x in (mass, radius, temperature, luminosity, delta))
+        B = len(M)
+        assert len(R) == len(T) == len(L) == len(D) == B
+        gran = np.ascontiguousarray(gran, dtype=np.float64)
+        modes = np.ascontiguousarray(modes, dtype=np.float64)
+        n_gran, n_modes = len(gran), len(modes)
+        assert gran.shape == (n_gran, 3) and modes.shape == (n_modes, 4 + n_gran)
+        al = None if alpha is None else np.ascontiguousarray(np.broadcast_to(alpha, (B,)), dtype=np.float64)
+        cap = B * (n_gran + n_modes)
+        j_off = np.zeros(B + 1, dtype=np.int64)
+        sho = np.empty((cap, 3)) if want_sho else None
+        coef = np.empty((cap, 4))
+        base = np.empty((cap, 4))
+        ddiag = np.empty(B)
+        self._check(self._lib.gf_feed_stars(
+            self._h, B, M.ctypes.data, R.ctypes.data, T.ctypes.data, L.ctypes.data,
+            None if al is None else al.ctypes.data, float(wavelength_nm), D.ctypes.data,
+            n_gran, gran.ctypes.data, n_modes, modes.ctypes.data, cap,
+            j_off.ctypes.data_as(_i64p), None if sho is None else sho.ctypes.data, coef.ctypes.data,
+            base.ctypes.data, ddiag.ctypes.data, 0))
+        self._inflight.clear()
+        n = int(j_off[-1])
+        return j_off, (None if sho is None else sho[:n]), coef[:n], base[:n], ddiag
+
+    def bandpass_amplitude(self, temperature, wl_um, transmittance):
+        """Bandpass amplitude ratio (Morris+ 2020 Eqn 11) of B temperatures on the device."""
+        T = np.ascontiguousarray(np.atleast_1d(temperature), dtype=np.float64)
+        wl = np.ascontiguousarray(wl_um, dtype=np.float64)
+        tr = np.ascontiguousarray(transmittance, dtype=np.float64)
+        assert wl.shape == tr.shape and wl.ndim == 1
+        out = np.empty(len(T))
+        self._check(self._lib.gf_bandpass_amplitude(self._h, len(T), T.ctypes.data, len(wl), wl.ctypes.data,
+                                                    tr.ctypes.data, out.ctypes.data, 0))
+        self._inflight.clear()
+        return out
 
     # -- K1 ----------------------------------------------------------------------------
     def loglike(self, kb, geom, t, y, diag=None, logdet=None, quad=None, status=None, flags=0):

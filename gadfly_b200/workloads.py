@@ -12,7 +12,7 @@ import time
 
 import numpy as np
 
-__all__ = ["star_table", "kepler_like_batch", "lattice_batch"]
+__all__ = ["star_table", "kepler_like_stars", "kepler_like_batch", "lattice_batch"]
 
 
 def star_table():
@@ -20,10 +20,9 @@ def star_table():
     return np.genfromtxt(path, delimiter=",", names=True, skip_header=1)
 
 
-def kepler_like_batch(n, seed):
-    """cfg2 / cfg5 population: rows drawn with replacement, jittered by their sig_* columns; built
-    by the batched feeder (gadfly_b200/feeder.py).  Returns (KernelBatch, feeder seconds)."""
-    from . import feeder
+def kepler_like_stars(n, seed):
+    """(M, R, T, L) of the cfg2 / cfg5 population: rows of the Huber-2011 table drawn with
+    replacement, jittered by their sig_* columns."""
     tab = star_table()
     rng = np.random.default_rng(seed)
     rows = rng.integers(0, len(tab), n)
@@ -33,8 +32,16 @@ def kepler_like_batch(n, seed):
     R = np.maximum(r["rad"] + z[:, 1] * r["sig_rad"], 0.3)
     T = np.maximum(r["teff"] + z[:, 2] * r["sig_teff"], 3500.0)
     L = np.maximum(r["lum"] + z[:, 3] * r["sig_lum"], 0.05)
+    return M, R, T, L
+
+
+def kepler_like_batch(n, seed, solver=None):
+    """cfg2 / cfg5 population built by the batched feeder (gadfly_b200/feeder.py): on the host, or
+    with ``solver=`` on that solver's GPU (csrc/feed.cu).  Returns (KernelBatch, feeder seconds)."""
+    from . import feeder
+    M, R, T, L = kepler_like_stars(n, seed)
     t0 = time.perf_counter()
-    kb = feeder.kernel_batch_for_stars(M, R, T, L, texp_s=60.0, bandpass='SOHO VIRGO')
+    kb = feeder.kernel_batch_for_stars(M, R, T, L, texp_s=60.0, bandpass='SOHO VIRGO', solver=solver)
     return kb, time.perf_counter() - t0
 
 

@@ -221,6 +221,32 @@ int gf_conditional_mean(gf_handle h, int64_t N, const double *t, int64_t M, cons
                         int64_t Jc, const double *coef, const double *alpha, double *mu,
                         uint32_t flags);
 
+/* ---- (f2) hyper-parameter feeder ------------------------------------------------------
+ * Stellar parameters -> kernel coefficients for B stars at once: the batched form of
+ * Hyperparameters.for_star (reference gadfly/core.py:107-333, scaling relations gadfly/scale.py) followed
+ * by the kernel assembly of StellarOscillatorKernel.__init__ (gadfly/core.py:345-394: celerite2
+ * SHOTerm.get_coefficients + TermConvolution.get_coefficients with its diagonal correction).
+ *   mass, radius, temperature, luminosity [B]  in M_sun, R_sun, K, L_sun
+ *   alpha [B] or NULL     bandpass amplitude ratio (gf_bandpass_amplitude; NULL = 1, flat bandpass)
+ *   wavelength_nm         mean wavelength of the bandpass (550 for a flat one)
+ *   delta [B]             exposure time in 1/uHz
+ *   gran  [n_gran][3]     solar (S0, w0, Q) of the granulation terms        } the solar fit the reference
+ *   modes [n_modes][4 + n_gran]  per solar p-mode: nu, Q, Gamma, unscaled   } ships as data/hyperparameters.json,
+ *                         height, background PSD of each granulation term   } reduced on the host once
+ * Outputs: j_off [B + 1] (HOST), and compacted in that CSR layout sho [.][3] = (S0, w0, Q) (may be NULL),
+ * coef [.][4] = (a', b', c, d), base [.][4] = (a, b, c, d) (may be NULL), ddiag [B]; the arrays hold
+ * cap_terms rows (B * (n_gran + n_modes) always suffices).  The reference drops scaled terms whose frequency
+ * or power is not positive; a kept term with Q < 0.5 is an error (GF_E_ARG). */
+int gf_feed_stars(gf_handle h, int64_t B, const double *mass, const double *radius, const double *temperature,
+                  const double *luminosity, const double *alpha, double wavelength_nm, const double *delta,
+                  int64_t n_gran, const double *gran, int64_t n_modes, const double *modes, int64_t cap_terms,
+                  int64_t *j_off, double *sho, double *coef, double *base, double *ddiag, uint32_t flags);
+/* Morris et al. (2020) Eqn 11 amplitude ratio of a tabulated bandpass for B effective temperatures
+ * (reference gadfly/scale.py:635-729): trapezoid quadratures of the Planck function and its temperature
+ * derivative over wl_um [n_wl] (micron) weighted by transmittance [n_wl] */
+int gf_bandpass_amplitude(gf_handle h, int64_t B, const double *temperature, int64_t n_wl, const double *wl_um,
+                          const double *transmittance, double *out, uint32_t flags);
+
 #ifdef __cplusplus
 }
 #endif

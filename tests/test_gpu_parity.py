@@ -609,3 +609,78 @@ def test_fit_with_device_gradients(solver):
     assert calls[0] < ll_true - 20.0            # the start is clearly worse than the truth
     assert -res.fun > ll_true - 5.0             # the fit is as good as the truth (12 parameters)
     assert np.all(np.abs(res.x[4:8] - x_true[4:8]) < np.array([0.5, 0.5, 2e-3, 2e-3]))   # frequencies recovered
+
+
+def test_device_feeder_matches_host_feeder(solver):
+    """(f2) csrc/feed.cu through gf_feed_stars against gadfly_b200/feeder.py (itself pinned to the
+    per-star ``Hyperparameters.for_star`` path and the mpmath fixture on the CPU side): 512
+    Kepler-like stars + the documentation's stars.  Same terms kept; (S0 w0 Q), a, b, Q to 1e-12
+    (w0, c, d on the scale of the star's highest frequency: the scaled mode frequencies are a
+    difference that can land near zero).  The exposure transform is celerite2's closed form, whose
+    cosh(w) cos(.) - 1 loses 1/|w|^2 (w = (c + i d) Delta) in ANY FP64 evaluation, so a', b' are
+    compared with that factor and on the scale of k(0); Delta-diag and log-likelihoods at a 10-min
+    exposure on stars where every term is resolved (|w| >= 1e-3)."""
+    from gadfly_b200 import feeder, workloads
+    M, R, T, L = workloads.kepler_like_stars(512, 4)
+    doc = np.array([(1.0, 1.0, 5777.0, 1.0), (0.9, 10.0, 4919.0, 52.3), (1.32, 11.26, 4923.0, 66.8),
+                    (1.1, 1.6, 6100.0, 3.2), (2.0, 20.7, 4364.0, 146.0)])
+    M, R, T, L = (np.concatenate([doc[:, k], x]) for k, x in enumerate((M, R, T, L)))
+    hpb = feeder.for_stars(M, R, T, L)
+    ref = feeder.kernel_batch_from_sho(hpb, 6e-5)
+    got, hp = feeder.kernel_batch_for_stars_device(solver, M, R, T, L, texp_s=60.0, return_hyperparameters=True)
+    assert np.array_equal(got.j_off, ref.j_off)
+    assert got.j_off[1] == 86 and got.j_off[2] - got.j_off[1] == 62           # Sun, KIC 9333184
+    widths = np.diff(ref.j_off)
+    star = np.repeat(np.arange(ref.B), widths)
+    w0max = np.maximum.reduceat(hpb.w0, ref.j_off[:-1])[star]
+    assert np.max(np.abs(hp.w0 - hpb.w0) / w0max) < 1e-13
+    np.testing.assert_allclose(hp.Q, hpb.Q, rtol=1e-13)
+    np.testing.assert_allclose(hp.S0 * hp.w0, hpb.S0 * hpb.w0, rtol=1e-12)
+    np.testing.assert_allclose(got.base[:, :2], ref.base[:, :2], rtol=1e-12)
+    assert np.max(np.abs(got.base[:, 2:] - ref.base[:, 2:]) / w0max[:, None]) < 1e-13
+    k0 = np.add.reduceat(np.abs(ref.coef[:, 0]), ref.j_off[:-1])
+    mag = np.hypot(ref.coef[:, 0], ref.coef[:, 1])
+    w = np.hypot(ref.coef[:, 2], ref.coef[:, 3]) * 6e-5
+    err = np.max(np.abs(got.coef[:, :2] - ref.coef[:, :2]), axis=1)
+    assert np.all(err <= 1e-13 * mag / np.minimum(w * w, 1.0) + 1e-11 * k0[star])
+    # Delta-diag and the log-likelihoods downstream, at a 10-min exposure, on the stars whose slowest
+    # term is still resolved (|w| >= 1e-3: the closed form keeps >= 10 digits)
+    ref10 = feeder.kernel_batch_from_sho(hpb, 6e-4)
+    got10 = feeder.kernel_batch_for_stars_device(solver, M, R, T, L, texp_s=600.0)
+    w10 = np.hypot(ref10.coef[:, 2], ref10.coef[:, 3]) * 6e-4
+    resolved = np.minimum.reduceat(w10, ref10.j_off[:-1]) >= 1e-3
+    assert resolved.sum() > 50
+    k10 = np.add.reduceat(np.abs(ref10.coef[:, 0]), ref10.j_off[:-1])
+    assert np.max(np.abs(got10.ddiag - ref10.ddiag)[resolved] / k10[resolved]) < 1e-9
+    idx = np.nonzero(resolved)[0][:6]
+    N = 4000
+    t = np.arange(N) * 6e-4
+    y = np.random.default_rng(8).standard_normal((len(idx), N)) * np.sqrt(k10[idx])[:, None]
+    ll_ref = batch.log_likelihood(ref10.take(idx), t, y, solver=solver)
+    ll_got = batch.log_likelihood(got10.take(idx), t, y, solver=solver)
+    np.testing.assert_allclose(ll_got, ll_ref, rtol=1e-9)
+    # KernelBatch.for_stars(solver=...) is the same call
+    kb = KernelBatch.for_stars(M[:5], R[:5], T[:5], L[:5], texp_s=60.0, solver=solver)
+    np.testing.assert_array_equal(kb.coef, got.take(np.arange(5)).coef)
+
+
+def test_device_bandpass_amplitude(solver):
+    """gf_bandpass_amplitude (Morris+ 2020 Eqn 11, reference gadfly/scale.py:635-729) against the
+    host quadrature on the same 10^4-point wavelength grid, and the feeder with a tabulated bandpass."""
+    from gadfly_b200 import feeder, scale
+
+    class Band:
+        wavelength = np.linspace(0.4, 0.9, 200)
+        transmittance = np.exp(-0.5 * ((np.linspace(0.4, 0.9, 200) - 0.65) / 0.1) ** 2)
+
+    filt = g.Filter(Band)
+    T = np.array([3900.0, 4400.0, 5000.0, 5777.0, 6500.0, 7200.0])
+    wl, tr = scale.bandpass_grid(filt)
+    got = solver.bandpass_amplitude(T, wl, tr)
+    ref = np.array([scale.amplitude_with_wavelength(filt, x) for x in T])
+    np.testing.assert_allclose(got, ref, rtol=1e-12)
+    M, R, L = np.ones(6), np.ones(6), (T / 5777.0) ** 4
+    kd = feeder.kernel_batch_for_stars_device(solver, M, R, T, L, bandpass=filt)
+    kh = feeder.kernel_batch_for_stars(M, R, T, L, bandpass=filt)
+    assert np.array_equal(kd.j_off, kh.j_off)
+    np.testing.assert_allclose(kd.base[:, 0], kh.base[:, 0], rtol=1e-11)

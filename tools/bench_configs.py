@@ -49,6 +49,8 @@ def main():
 
     # ---- cfg2 -------------------------------------------------------------------------------
     kb, host_s = kepler_like_batch(args.stars, 1)
+    kepler_like_batch(8, 1, solver=solver)
+    _, dev_s = kepler_like_batch(args.stars, 1, solver=solver)
     # white measurement noise yerr = 50 ppm as a scalar diagonal (added to the per-star ddiag):
     # without it ~7 % of these stars (slow red giants at 1-min cadence, k(0) ~ 1e7 ppm^2) are
     # numerically not positive definite -- the CPU oracle reports the same pivots <= 0, and
@@ -83,7 +85,7 @@ def main():
     out["cfg2"] = dict(stars=B, not_positive_definite=int(bad.sum()), n_points=N, J_min=int(J.min()), J_mean=float(J.mean()), J_max=int(J.max()),
                        kernel_ms=ms, light_curves_per_s=B / (ms * 1e-3),
                        updates_per_s=float(np.sum(J * J)) * N / (ms * 1e-3),
-                       fp64_frac=flops / (ms * 1e-3) / peak, host_feeder_s=host_s)
+                       fp64_frac=flops / (ms * 1e-3) / peak, host_feeder_s=host_s, device_feeder_s=dev_s)
     print("cfg2", json.dumps(out["cfg2"]), flush=True)
     del y
 
