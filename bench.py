@@ -193,7 +193,9 @@ def leg_cfg4(args, solver, dev, rank, world, peak):
     G, N = args.grid, 100000
     bounds = batch.shard_bounds(np.ones(G), world)
     lo, hi = int(bounds[rank]), int(bounds[rank + 1])
-    kb, feeder_s = workloads.lattice_batch(G, 3, lo, hi)
+    _, host_feeder_s = workloads.lattice_batch(G, 3, lo, hi)               # host feeder, for the record
+    workloads.lattice_batch(G, 3, lo, min(hi, lo + 8), solver=solver)      # warm-up of the device feeder
+    kb, feeder_s = workloads.lattice_batch(G, 3, lo, hi, solver=solver)
     J = kb.J.astype(np.float64)
     gen = torch.Generator(device=dev)
     gen.manual_seed(3)                                   # the same light curve on every rank
@@ -222,7 +224,7 @@ def leg_cfg4(args, solver, dev, rank, world, peak):
     other = (rank + 1) % world
     s_lo = int(bounds[other])
     s_n = min(8, int(bounds[other + 1]) - s_lo)
-    ks, _ = workloads.lattice_batch(G, 3, s_lo, s_lo + s_n)
+    ks, _ = workloads.lattice_batch(G, 3, s_lo, s_lo + s_n, solver=solver)
     ll_s = batch.log_likelihood(ks, t, y, solver=solver, flags=S.FLAG_SHARED_Y)
     got = ll_all[s_lo:s_lo + s_n].cpu().numpy()
     assert np.array_equal(got, ll_s), (got, ll_s)
@@ -235,7 +237,7 @@ def leg_cfg4(args, solver, dev, rank, world, peak):
                 gather=dict(collective="all_gather_into_tensor (NCCL)" if world > 1 else "none (1 rank)",
                             in_timed_region=True, bytes_per_rank=int(B * 12), verified=f"{s_n} grid points of rank "
                             f"{other} recomputed on rank {rank}: bit-identical"),
-                host_feeder_s=feeder_s)
+                host_feeder_s=host_feeder_s, device_feeder_s=feeder_s)
 
 
 def leg_cfg5(args, solver, dev, rank, world, peak):

@@ -50,6 +50,9 @@ cudaError_t launch_feed_hyper(const FeedArgs &A, double *sho_all, unsigned char 
 cudaError_t launch_feed_coef(const FeedArgs &A, const double *sho_all, const unsigned char *keep_all,
                              const int64_t *j_off, double *sho, double *coef, double *base, double *ddiag,
                              cudaStream_t stream);
+cudaError_t launch_feed_sho(int64_t B, const int64_t *j_off, const double *sho, const double *delta,
+                            double *coef, double *base, double *dterm, double *ddiag, int32_t *overdamped,
+                            cudaStream_t stream);
 cudaError_t launch_bandpass(int64_t B, const double *T, int64_t n_wl, const double *wl, const double *filt,
                             double *out, cudaStream_t stream);
 cudaError_t launch_bin_power(int64_t B, int64_t F, int64_t nb, const int64_t *lo, const int64_t *cnt,
@@ -1085,6 +1088,47 @@ int gf_feed_stars(gf_handle h, int64_t B, const double *mass, const double *radi
     GF_CUDA(h, end_kernel(h));
     GF_CUDA(h, finish_out(h, o_dd));
     GF_CUDA(h, finish_out(h, o_sho));
+    GF_CUDA(h, finish_out(h, o_coef));
+    GF_CUDA(h, finish_out(h, o_base));
+    GF_CUDA(h, finish_call(h, flags));
+    return GF_OK;
+}
+
+int gf_feed_sho(gf_handle h, int64_t B, const int64_t *j_off, const double *sho, const double *delta,
+                double *coef, double *base, double *ddiag, uint32_t flags)
+{
+    if (!h) return GF_E_ARG;
+    if (B < 0) return fail(h, GF_E_ARG, "negative size");
+    if (B == 0) return GF_OK;
+    if (!j_off || !sho || !delta || !coef || !ddiag) return fail(h, GF_E_ARG, "null data pointer");
+    if (j_off[0] != 0) return fail(h, GF_E_ARG, "offsets must start at 0");
+    for (int64_t b = 0; b < B; ++b)
+        if (j_off[b + 1] < j_off[b]) return fail(h, GF_E_ARG, "offsets must be non-decreasing");
+    const int64_t total = j_off[B];
+    Guard guard(h);
+    const int64_t *d_joff;
+    const double *d_sho, *d_delta;
+    GF_CUDA(h, stage_in(h, S_JOFF, j_off, (size_t)B + 1, &d_joff));
+    GF_CUDA(h, stage_in(h, S_FSHOALL, sho, (size_t)total * 3, &d_sho));
+    GF_CUDA(h, stage_in(h, S_DELTA, delta, (size_t)B, &d_delta));
+    void *dterm = nullptr, *over = nullptr;
+    GF_CUDA(h, reserve(h, S_FKEEP, (size_t)std::max<int64_t>(total, 1) * sizeof(double), &dterm));
+    GF_CUDA(h, reserve(h, S_FCOUNT, sizeof(int32_t), &over));
+    Out<double> o_coef, o_base, o_dd;
+    GF_CUDA(h, stage_out(h, S_OUT, coef, (size_t)total * 4, &o_coef));
+    GF_CUDA(h, stage_out(h, S_FBASE, base, (size_t)total * 4, &o_base));
+    GF_CUDA(h, stage_out(h, S_FDDIAG, ddiag, (size_t)B, &o_dd));
+    GF_CUDA(h, begin_kernel(h));
+    GF_CUDA(h, cudaMemsetAsync(over, 0, sizeof(int32_t), h->stream));
+    GF_CUDA(h, gf::launch_feed_sho(B, d_joff, d_sho, d_delta, o_coef.dev, o_base.dev, (double *)dterm, o_dd.dev,
+                                   (int32_t *)over, h->stream));
+    h->launches += 1;
+    GF_CUDA(h, end_kernel(h));
+    int32_t n_over = 0;
+    GF_CUDA(h, cudaMemcpyAsync(&n_over, over, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    GF_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (n_over) return fail(h, GF_E_ARG, "overdamped term (Q < 0.5): build that kernel per star");
+    GF_CUDA(h, finish_out(h, o_dd));
     GF_CUDA(h, finish_out(h, o_coef));
     GF_CUDA(h, finish_out(h, o_base));
     GF_CUDA(h, finish_call(h, flags));

@@ -8,6 +8,7 @@
 //   hyper_kernel     one CTA per star, one thread per solar term: scaled (S0, w0, Q) and the keep mask
 //                    (the reference drops terms whose scaled frequency or power is not positive), count
 //   coef_kernel      one CTA per star: compaction to the CSR layout, (a, b, c, d), (a', b'), Delta-diag
+//   coef_csr_kernel  the same arithmetic for (S0, w0, Q) already in CSR layout, one warp per kernel
 //   bandpass_kernel  one CTA per star: four Planck-weighted quadratures over the wavelength grid
 //
 // The arithmetic follows gadfly_b200/feeder.py (the vectorised host restatement) operation by operation.
@@ -130,6 +131,42 @@ hyper_kernel(FeedArgs A, double *sho_all, unsigned char *keep_all, int32_t *coun
     }
 }
 
+// One SHO term -> (a, b, c, d), (a', b') and its share of the diagonal correction.
+// SHOTerm.get_coefficients, underdamped branch (eps = 1e-5 as in celerite2), then the
+// exposure-time transform in the expression order of terms.TermConvolution: it is
+// cancellation-sensitive, so nothing here is contracted into FMAs.
+struct TermCoef { double a, b, c, d, a_new, b_new, dterm; };
+__device__ TermCoef term_coefficients(double S0, double w0, double Q, double dt)
+{
+    const double f = sqrt(fmax(__dsub_rn(__dmul_rn(4.0, __dmul_rn(Q, Q)), 1.0), 1e-5));
+    const double a = S0 * w0 * Q;
+    const double bb = a / f;
+    const double c = 0.5 * w0 / Q;
+    const double d = c * f;
+    const double cd = __dmul_rn(c, dt), dd = __dmul_rn(d, dt);
+    const double c2 = __dmul_rn(c, c), d2 = __dmul_rn(d, d);
+    const double c2pd2 = __dadd_rn(c2, d2), c2md2 = __dsub_rn(c2, d2);
+    const double q = __dmul_rn(dt, c2pd2);
+    const double factor = 2.0 / __dmul_rn(q, q);
+    const double ch = cosh(cd), sh = sinh(cd);
+    double sn, cs;
+    sincos(dd, &sn, &cs);
+    const double cos_term = __dsub_rn(__dmul_rn(ch, cs), 1.0);
+    const double sin_term = __dmul_rn(sh, sn);
+    const double C1 = __dadd_rn(__dmul_rn(a, c2md2), __dmul_rn(__dmul_rn(__dmul_rn(2.0, bb), c), d));
+    const double C2 = __dsub_rn(__dmul_rn(bb, c2md2), __dmul_rn(__dmul_rn(__dmul_rn(2.0, a), c), d));
+    TermCoef r;
+    r.a = a; r.b = bb; r.c = c; r.d = d;
+    r.a_new = __dmul_rn(factor, __dsub_rn(__dmul_rn(C1, cos_term), __dmul_rn(C2, sin_term)));
+    r.b_new = __dmul_rn(factor, __dadd_rn(__dmul_rn(C2, cos_term), __dmul_rn(C1, sin_term)));
+    const double norm = __dmul_rn(q, q);
+    const double acbd = __dadd_rn(__dmul_rn(a, c), __dmul_rn(bb, d));
+    const double num = __dadd_rn(__dsub_rn(__dmul_rn(__dmul_rn(C2, ch), sn), __dmul_rn(__dmul_rn(C1, sh), cs)),
+                                 __dmul_rn(__dmul_rn(acbd, dt), c2pd2));
+    r.dterm = num / norm;
+    return r;
+}
+
 __global__ void __launch_bounds__(FEED_THREADS)
 coef_kernel(FeedArgs A, const double *sho_all, const unsigned char *keep_all, const int64_t *j_off,
             double *sho, double *coef, double *base, double *ddiag)
@@ -151,38 +188,12 @@ coef_kernel(FeedArgs A, const double *sho_all, const unsigned char *keep_all, co
         if (keep) {
             const double *s = sho_all + ((size_t)b * nt + i) * 3;
             const double S0 = s[0], w0 = s[1], Q = s[2];
-            const double dt = A.delta[b];
-            // SHOTerm -> (a, b, c, d), underdamped branch, eps = 1e-5 as in celerite2
-            const double f = sqrt(fmax(__dsub_rn(__dmul_rn(4.0, __dmul_rn(Q, Q)), 1.0), 1e-5));
-            const double a = S0 * w0 * Q;
-            const double bb = a / f;
-            const double c = 0.5 * w0 / Q;
-            const double d = c * f;
-            // exposure-time transform in the expression order of terms.TermConvolution:
-            // cancellation-sensitive, so no contraction into FMAs here
-            const double cd = __dmul_rn(c, dt), dd = __dmul_rn(d, dt);
-            const double c2 = __dmul_rn(c, c), d2 = __dmul_rn(d, d);
-            const double c2pd2 = __dadd_rn(c2, d2), c2md2 = __dsub_rn(c2, d2);
-            const double q = __dmul_rn(dt, c2pd2);
-            const double factor = 2.0 / __dmul_rn(q, q);
-            const double ch = cosh(cd), sh = sinh(cd);
-            double sn, cs;
-            sincos(dd, &sn, &cs);
-            const double cos_term = __dsub_rn(__dmul_rn(ch, cs), 1.0);
-            const double sin_term = __dmul_rn(sh, sn);
-            const double C1 = __dadd_rn(__dmul_rn(a, c2md2), __dmul_rn(__dmul_rn(__dmul_rn(2.0, bb), c), d));
-            const double C2 = __dsub_rn(__dmul_rn(bb, c2md2), __dmul_rn(__dmul_rn(__dmul_rn(2.0, a), c), d));
-            const double a_new = __dmul_rn(factor, __dsub_rn(__dmul_rn(C1, cos_term), __dmul_rn(C2, sin_term)));
-            const double b_new = __dmul_rn(factor, __dadd_rn(__dmul_rn(C2, cos_term), __dmul_rn(C1, sin_term)));
-            const double norm = __dmul_rn(q, q);
-            const double acbd = __dadd_rn(__dmul_rn(a, c), __dmul_rn(bb, d));
-            const double num = __dadd_rn(__dsub_rn(__dmul_rn(__dmul_rn(C2, ch), sn), __dmul_rn(__dmul_rn(C1, sh), cs)),
-                                         __dmul_rn(__dmul_rn(acbd, dt), c2pd2));
-            dterm_s[rank] = num / norm;
+            const TermCoef r = term_coefficients(S0, w0, Q, A.delta[b]);
+            dterm_s[rank] = r.dterm;
             const size_t row = (size_t)j_off[b] + rank;
             if (sho) { sho[3 * row] = S0; sho[3 * row + 1] = w0; sho[3 * row + 2] = Q; }
-            if (base) { base[4 * row] = a; base[4 * row + 1] = bb; base[4 * row + 2] = c; base[4 * row + 3] = d; }
-            coef[4 * row] = a_new; coef[4 * row + 1] = b_new; coef[4 * row + 2] = c; coef[4 * row + 3] = d;
+            if (base) { base[4 * row] = r.a; base[4 * row + 1] = r.b; base[4 * row + 2] = r.c; base[4 * row + 3] = r.d; }
+            coef[4 * row] = r.a_new; coef[4 * row + 1] = r.b_new; coef[4 * row + 2] = r.c; coef[4 * row + 3] = r.d;
         }
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -191,6 +202,36 @@ coef_kernel(FeedArgs A, const double *sho_all, const unsigned char *keep_all, co
             ddiag[b] = 2 * s;
         }
         __syncthreads();
+    }
+}
+
+// (S0, w0, Q) already in CSR layout (a hyper-parameter lattice, the perturbed kernels of a gradient):
+// one warp per kernel, lanes stride over its terms; Delta-diag summed in term order by lane 0 of a
+// per-term scratch so that the result does not depend on the launch shape.
+__global__ void __launch_bounds__(FEED_THREADS)
+coef_csr_kernel(int64_t B, const int64_t *j_off, const double *sho, const double *delta, double *coef,
+                double *base, double *dterm, double *ddiag, int32_t *overdamped)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (int64_t)blockIdx.x * (FEED_THREADS / 32) + (threadIdx.x >> 5);
+    const int64_t nwarp = (int64_t)gridDim.x * (FEED_THREADS / 32);
+    for (int64_t b = warp0; b < B; b += nwarp) {
+        const int64_t j0 = j_off[b], j1 = j_off[b + 1];
+        const double dt = delta[b];
+        for (int64_t j = j0 + lane; j < j1; j += 32) {
+            const double Q = sho[3 * j + 2];
+            if (Q < 0.5) atomicAdd(overdamped, 1);
+            const TermCoef r = term_coefficients(sho[3 * j], sho[3 * j + 1], Q, dt);
+            if (base) { base[4 * j] = r.a; base[4 * j + 1] = r.b; base[4 * j + 2] = r.c; base[4 * j + 3] = r.d; }
+            coef[4 * j] = r.a_new; coef[4 * j + 1] = r.b_new; coef[4 * j + 2] = r.c; coef[4 * j + 3] = r.d;
+            dterm[j] = r.dterm;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            double s = 0.0;
+            for (int64_t j = j0; j < j1; ++j) s += dterm[j];
+            ddiag[b] = 2 * s;
+        }
     }
 }
 
@@ -273,6 +314,16 @@ cudaError_t launch_feed_coef(const FeedArgs &A, const double *sho_all, const uns
 {
     const unsigned grid = (unsigned)std::min<int64_t>(A.B, 1 << 20);
     coef_kernel<<<grid, FEED_THREADS, 0, stream>>>(A, sho_all, keep_all, j_off, sho, coef, base, ddiag);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_feed_sho(int64_t B, const int64_t *j_off, const double *sho, const double *delta,
+                            double *coef, double *base, double *dterm, double *ddiag, int32_t *overdamped,
+                            cudaStream_t stream)
+{
+    const int64_t blocks = (B + FEED_THREADS / 32 - 1) / (FEED_THREADS / 32);
+    const unsigned grid = (unsigned)std::min<int64_t>(blocks, 1 << 20);
+    coef_csr_kernel<<<grid, FEED_THREADS, 0, stream>>>(B, j_off, sho, delta, coef, base, dterm, ddiag, overdamped);
     return cudaGetLastError();
 }
 

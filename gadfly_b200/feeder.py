@@ -185,7 +185,7 @@ def for_stars(mass, radius, temperature, luminosity, bandpass='SOHO VIRGO', alph
     return HyperparameterBatch(S0[keep], w0[keep], Q[keep], j_off, deg[keep])
 
 
-def kernel_batch_from_sho(hpb, delta, eps=1e-5):
+def kernel_batch_from_sho(hpb, delta, eps=1e-5, solver=None):
     """``KernelBatch`` of ``StellarOscillatorKernel(hyperparameters, delta=...)`` for every star of
     a :class:`HyperparameterBatch` (delta: exposure in 1/uHz, scalar or [B]).
 
@@ -201,6 +201,13 @@ def kernel_batch_from_sho(hpb, delta, eps=1e-5):
     widths = np.diff(j_off)
     if B and int(widths.max()) * 2 > GF_MAX_J_WIDE:
         raise ValueError(f"kernel state wider than GF_MAX_J_WIDE = {GF_MAX_J_WIDE}")
+    if solver is not None:          # the same arithmetic on that solver's GPU (csrc/feed.cu, gf_feed_sho)
+        kb = object.__new__(KernelBatch)
+        kb.B = B
+        kb.coef, kb.base, kb.ddiag = solver.feed_sho(j_off, S0, w0, Q, delta)
+        kb.j_off = j_off.copy()
+        kb.delta = delta
+        return kb
     f = np.sqrt(np.maximum(4.0 * Q ** 2 - 1.0, eps))
     a = S0 * w0 * Q
     b = a / f

@@ -107,6 +107,8 @@ _SIGNATURES = {
         ctypes.c_void_p, ctypes.c_int64, _f64p, _f64p, _f64p, _f64p, _f64p, ctypes.c_double, _f64p,
         ctypes.c_int64, _f64p, ctypes.c_int64, _f64p, ctypes.c_int64, _i64p, _f64p, _f64p, _f64p, _f64p,
         ctypes.c_uint32]),
+    "gf_feed_sho": (ctypes.c_int, [
+        ctypes.c_void_p, ctypes.c_int64, _i64p, _f64p, _f64p, _f64p, _f64p, _f64p, ctypes.c_uint32]),
     "gf_bandpass_amplitude": (ctypes.c_int, [
         ctypes.c_void_p, ctypes.c_int64, _f64p, ctypes.c_int64, _f64p, _f64p, _f64p, ctypes.c_uint32]),
     "gf_conditional_mean": (ctypes.c_int, [
@@ -412,6 +414,20 @@ class Solver:
         self._inflight.clear()
         n = int(j_off[-1])
         return j_off, (None if sho is None else sho[:n]), coef[:n], base[:n], ddiag
+
+    def feed_sho(self, j_off, S0, w0, Q, delta):
+        """(S0, w0, Q) in CSR layout -> (coef, base, ddiag) on the device (gf_feed_sho)."""
+        j_off = np.ascontiguousarray(j_off, dtype=np.int64)
+        B = len(j_off) - 1
+        sho = np.ascontiguousarray(np.stack([S0, w0, Q], axis=1), dtype=np.float64)
+        n = int(j_off[-1])
+        assert sho.shape == (n, 3)
+        D = np.ascontiguousarray(np.broadcast_to(delta, (B,)), dtype=np.float64)
+        coef, base, ddiag = np.empty((n, 4)), np.empty((n, 4)), np.empty(B)
+        self._check(self._lib.gf_feed_sho(self._h, B, j_off.ctypes.data_as(_i64p), sho.ctypes.data, D.ctypes.data,
+                                          coef.ctypes.data, base.ctypes.data, ddiag.ctypes.data, 0))
+        self._inflight.clear()
+        return coef, base, ddiag
 
     def bandpass_amplitude(self, temperature, wl_um, transmittance):
         """Bandpass amplitude ratio (Morris+ 2020 Eqn 11) of B temperatures on the device."""

@@ -45,10 +45,11 @@ def kepler_like_batch(n, seed, solver=None):
     return kb, time.perf_counter() - t0
 
 
-def lattice_batch(n, seed, lo=0, hi=None):
+def lattice_batch(n, seed, lo=0, hi=None, solver=None):
     """cfg4 grid: solar hyper-parameters with S0, w0, Q of every term scaled by lattice factors
     0.9 .. 1.1 (a random subset of n points of the side^3 lattice).  ``lo, hi``: build only the grid
-    points [lo, hi) of that list (a rank's shard).  Returns (KernelBatch, feeder seconds)."""
+    points [lo, hi) of that list (a rank's shard); ``solver=``: coefficients on that solver's GPU
+    (gf_feed_sho).  Returns (KernelBatch, feeder seconds)."""
     from . import feeder
     from .core import Hyperparameters
     hp = Hyperparameters.for_sun()
@@ -62,5 +63,5 @@ def lattice_batch(n, seed, lo=0, hi=None):
     hpb = feeder.HyperparameterBatch((S0[None, :] * f[i][:, None]).ravel(), (w0[None, :] * f[j][:, None]).ravel(),
                                      (Q[None, :] * f[k][:, None]).ravel(),
                                      np.arange(m + 1, dtype=np.int64) * len(S0))
-    kb = feeder.kernel_batch_from_sho(hpb, 6e-5)
+    kb = feeder.kernel_batch_from_sho(hpb, 6e-5, solver=solver)
     return kb, time.perf_counter() - t0

@@ -241,6 +241,12 @@ int gf_feed_stars(gf_handle h, int64_t B, const double *mass, const double *radi
                   const double *luminosity, const double *alpha, double wavelength_nm, const double *delta,
                   int64_t n_gran, const double *gran, int64_t n_modes, const double *modes, int64_t cap_terms,
                   int64_t *j_off, double *sho, double *coef, double *base, double *ddiag, uint32_t flags);
+/* The kernel-assembly half alone, for hyper-parameters that are already (S0, w0, Q) in CSR layout (a
+ * hyper-parameter lattice, the perturbed kernels of a finite-difference gradient): sho [j_off[B]][3] ->
+ * coef, base (may be NULL) [j_off[B]][4], ddiag [B]; celerite2 SHOTerm.get_coefficients +
+ * TermConvolution.get_coefficients as called from reference gadfly/core.py:345-394.  Q < 0.5: GF_E_ARG. */
+int gf_feed_sho(gf_handle h, int64_t B, const int64_t *j_off, const double *sho, const double *delta,
+                double *coef, double *base, double *ddiag, uint32_t flags);
 /* Morris et al. (2020) Eqn 11 amplitude ratio of a tabulated bandpass for B effective temperatures
  * (reference gadfly/scale.py:635-729): trapezoid quadratures of the Planck function and its temperature
  * derivative over wl_um [n_wl] (micron) weighted by transmittance [n_wl] */

@@ -684,3 +684,46 @@ def test_device_bandpass_amplitude(solver):
     kh = feeder.kernel_batch_for_stars(M, R, T, L, bandpass=filt)
     assert np.array_equal(kd.j_off, kh.j_off)
     np.testing.assert_allclose(kd.base[:, 0], kh.base[:, 0], rtol=1e-11)
+
+
+def test_device_sho_to_coefficients(solver):
+    """gf_feed_sho: (S0, w0, Q) in CSR layout -> coefficients, against feeder.kernel_batch_from_sho on
+    a slice of the cfg4 lattice (solar kernel, J = 172) and on a ragged batch; a', b' within the
+    rounding of the closed form (1/|w|^2, see test_device_feeder_matches_host_feeder), Delta-diag on
+    the scale of k(0); overdamped terms are refused like on the host."""
+    from gadfly_b200 import feeder, workloads
+    ref, _ = workloads.lattice_batch(64, 3)
+    got, _ = workloads.lattice_batch(64, 3, solver=solver)
+    assert np.array_equal(got.j_off, ref.j_off)
+    np.testing.assert_allclose(got.base, ref.base, rtol=1e-13)
+    star = np.repeat(np.arange(ref.B), np.diff(ref.j_off))
+    k0 = np.add.reduceat(np.abs(ref.coef[:, 0]), ref.j_off[:-1])
+    mag = np.hypot(ref.coef[:, 0], ref.coef[:, 1])
+    w = np.hypot(ref.coef[:, 2], ref.coef[:, 3]) * 6e-5
+    err = np.max(np.abs(got.coef[:, :2] - ref.coef[:, :2]), axis=1)
+    assert np.all(err <= 1e-13 * mag / np.minimum(w * w, 1.0) + 1e-11 * k0[star])
+    np.testing.assert_array_equal(got.coef[:, 2:], got.base[:, 2:])
+    assert np.max(np.abs(got.ddiag - ref.ddiag) / k0) < 1e-13 / np.min(w) ** 2
+    # ragged widths, per-kernel exposure times
+    rng = np.random.default_rng(12)
+    widths = rng.integers(1, 100, 37)
+    j_off = np.concatenate([[0], np.cumsum(widths)])
+    n = int(j_off[-1])
+    hpb = feeder.HyperparameterBatch(rng.uniform(0.1, 100, n), rng.uniform(50.0, 3e4, n), rng.uniform(0.5, 900, n), j_off)
+    delta = rng.uniform(2e-4, 1e-3, 37)
+    r2 = feeder.kernel_batch_from_sho(hpb, delta)
+    g2 = feeder.kernel_batch_from_sho(hpb, delta, solver=solver)
+    np.testing.assert_allclose(g2.base, r2.base, rtol=1e-13)
+    k2 = np.add.reduceat(np.abs(r2.coef[:, 0]), j_off[:-1])
+    s2 = np.repeat(np.arange(37), widths)
+    assert np.max(np.abs(g2.coef[:, :2] - r2.coef[:, :2]) / k2[s2, None]) < 1e-10
+    assert np.max(np.abs(g2.ddiag - r2.ddiag) / k2) < 1e-9
+    t = np.arange(1500) * 4e-4
+    y = rng.standard_normal((37, 1500)) * np.sqrt(k2)[:, None]
+    np.testing.assert_allclose(batch.log_likelihood(g2, t, y, solver=solver),
+                               batch.log_likelihood(r2, t, y, solver=solver), rtol=1e-9)
+    bad = feeder.HyperparameterBatch([1.0, 1.0], [100.0, 200.0], [0.7, 0.4], [0, 2])
+    with pytest.raises(ValueError):
+        feeder.kernel_batch_from_sho(bad, 6e-5, solver=solver)
+    with pytest.raises(ValueError):
+        solver.feed_sho(np.array([0, 2]), [1.0, 1.0], [100.0, 200.0], [0.7, 0.4], 6e-5)
