@@ -44,6 +44,8 @@ FftPlan *new_fft_plan();
 void delete_fft_plan(FftPlan *fp);
 cudaError_t launch_obs_power(FftPlan *fp, int64_t B, int64_t N, const double *flux, double d, int include_zero,
                              double2 *spec, double *power, cudaStream_t stream);
+bool scan_blk_supports(int mode, int jmax);
+cudaError_t launch_scan_blk(int mode, const ScanArgs &args, int sm_count, cudaStream_t stream);
 int feed_max_terms();
 cudaError_t launch_feed_hyper(const FeedArgs &A, double *sho_all, unsigned char *keep_all, int32_t *count,
                               cudaStream_t stream);
@@ -478,6 +480,9 @@ int run_scan(gf_handle h, int mode, int64_t B, const int64_t *n_off, const int64
             void *state = nullptr;
             GF_CUDA(h, reserve(h, S_WIDE, gf::scan_wide_state_bytes(grid), &state));
             GF_CUDA(h, gf::launch_scan_wide(mode, A, grid, (double *)state, h->stream));
+            h->launches += 1;
+        } else if ((flags & GF_FLAG_BLOCKED) && !ref && gf::scan_blk_supports(mode, g.jmax)) {
+            GF_CUDA(h, gf::launch_scan_blk(mode, A, h->sm_count, h->stream));
             h->launches += 1;
         } else if (ref) {
             int grid = (int)std::min<int64_t>(B, (int64_t)h->sm_count);

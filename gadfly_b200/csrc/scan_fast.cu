@@ -1211,6 +1211,7 @@ cudaError_t launch_mode(const ScanArgs &args, int grid, cudaStream_t stream)
 
 }  // namespace
 
+#ifndef GF_SCAN_FAST_AS_HEADER   // scan_blk.cu includes this file for the producer warp and the tile map
 bool scan_fast_supports(int mode, int jmax)
 {
     (void)mode;
@@ -1229,5 +1230,7 @@ cudaError_t launch_scan_fast(int mode, const ScanArgs &args, int jmax, int sm_co
     default:           return launch_mode<MODE_FACTOR>(args, grid, stream);
     }
 }
+
+#endif  // GF_SCAN_FAST_AS_HEADER
 
 }  // namespace gf

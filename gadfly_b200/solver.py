@@ -34,6 +34,7 @@ FLAG_ASYNC = 1
 FLAG_REFERENCE_ORDER = 2
 FLAG_SHARED_Y = 4
 FLAG_WIDE_KERNEL = 8
+FLAG_BLOCKED = 16
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIBNAME = "libgadfly_b200.so"

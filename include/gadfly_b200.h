@@ -79,6 +79,8 @@ enum {
 #define GF_FLAG_REFERENCE_ORDER 2u /* use the simple reference-order scan kernel (validation) */
 #define GF_FLAG_WIDE_KERNEL 8u     /* do not take the one-warp-per-sequence path for narrow batches
                                       (all J <= 32); validation of that path against the wide kernel */
+#define GF_FLAG_BLOCKED 16u        /* experimental: the 4-step blocked scan kernel (csrc/scan_blk.cu) for
+                                      gf_loglike_batched / gf_sample_batched */
 #define GF_FLAG_SHARED_Y 4u        /* y / diag (gf_loglike_batched) are laid out like t: sequence b
                                       reads y[t_off[b] + n], so that one light curve serves many
                                       hyper-parameter sets (stride-0 descriptor of SURVEY.md 8b) */

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import gadfly_b200 as g
-from gadfly_b200 import batch
+from gadfly_b200 import batch, solver as S
 from gadfly_b200.solver import Geometry, KernelBatch
 import oracle
 
@@ -273,3 +273,41 @@ def test_kernels_wider_than_the_register_resident_scans(solver, solar_kernel):
     too_many = list(solar_kernel.term.terms) * 3
     with pytest.raises(ValueError):
         KernelBatch([g.StellarOscillatorKernel(terms=too_many, delta=solar_kernel.delta)])
+
+
+def test_blocked_scan_kernel_matches_oracle(solver, solar_kernel):
+    """GF_FLAG_BLOCKED (csrc/scan_blk.cu): the 4-step blocked recurrence -- rank-4 updates, four
+    matrix-vector products against the same state, one batch of dot products and a scalar 4 x 4
+    recursion per hand-over -- is the arithmetic of the step-by-step recurrence up to summation order.
+    Experimental (bulk-synchronous, slower than the default kernel): checked here
+    against the oracle on a cadence with gaps (frame changes inside ring halves, blocks cut short),
+    lengths that are not multiples of 4, a mixed-width batch, and a not-positive-definite case."""
+    from gadfly_b200 import philox
+    rng = np.random.default_rng(21)
+    narrow = g.StellarOscillatorKernel(terms=list(solar_kernel.term.terms)[:30], delta=solar_kernel.delta)
+    for N, kernels in ((1, [solar_kernel]), (6, [solar_kernel, narrow]), (1003, [solar_kernel, narrow, solar_kernel])):
+        t = np.cumsum(rng.choice([6e-5, 6e-5, 6e-5, 1.2e-4, 3e-3, 0.4], N))
+        B = len(kernels)
+        kb = KernelBatch(kernels)
+        geom = Geometry.shared_t(B, N)
+        diag = np.full(B * N, 20.0 ** 2)
+        y = rng.standard_normal(B * N) * 300.0
+        ld, q, st = solver.loglike(kb, geom, t, y, diag=diag, flags=S.FLAG_BLOCKED)
+        x, _, sx = solver.sample(kb, geom, t, diag=diag, seed=4, flags=S.FLAG_BLOCKED)
+        for b, kern in enumerate(kernels):
+            scan = kern.scan_coefficients()
+            ref = oracle.stream(0, scan, t, y[b * N:(b + 1) * N], diag=diag[:N])
+            assert st[b] == 0 and ref[2] == 0
+            assert ld[b] == pytest.approx(ref[0], rel=1e-9)
+            assert q[b] == pytest.approx(ref[1], rel=1e-9)
+            xr = oracle.stream(1, scan, t, philox.normals(4, b, N), diag=diag[:N])[0]
+            assert np.max(np.abs(x[b * N:(b + 1) * N] - xr)) <= 1e-9 * np.max(np.abs(xr))
+    # first non-positive pivot: same row as the default kernel and the oracle report
+    N = 700
+    t = np.arange(N) * 6e-5
+    bad = np.full(N, 25.0); bad[333:] = -4.0e5
+    kb = KernelBatch([solar_kernel])
+    y = rng.standard_normal(N) * 300.0
+    _, _, st_blk = solver.loglike(kb, Geometry.shared_t(1, N), t, y, diag=bad, flags=S.FLAG_BLOCKED)
+    _, _, st_def = solver.loglike(kb, Geometry.shared_t(1, N), t, y, diag=bad)
+    assert st_blk[0] == st_def[0] == oracle.stream(0, solar_kernel.scan_coefficients(), t, y, diag=bad)[2] > 0
