@@ -29,7 +29,11 @@ namespace {
 
 constexpr int KB = 4;                                     // rows per block
 constexpr int BLK_THREADS = MAT_THREADS + CH_THREADS;     // everybody but the producer warp
-constexpr int BAR_D = 10, BAR_A = 11, BAR_B = 12, BAR_C = 13;
+// hand-overs between the matrix warps (bar.arrive / bar.sync with all 352 threads counted):
+constexpr int BAR_S1 = 10;    // partial products of a block are in P            [matrix -> chain]
+constexpr int BAR_S2 = 11;    // t~, w~ of the previous block are in T2 / W2       [chain -> matrix]
+constexpr int BAR_S3 = 12;    // P consumed; rows / frame / descriptor of the next block ready  [chain -> matrix]
+constexpr int BAR_S4 = 13;    // the update is applied, T2 / W2 may be rewritten   [matrix -> chain]
 
 struct BlkSmem {
     double P23[2][NSLOT][JP_MAX];      // partial sums of rows 2, 3 of a block (rows 0, 1: FastSmem::P)
@@ -37,11 +41,11 @@ struct BlkSmem {
     double2 T2[KB][4][NB_PAD];         // t~ of the previous block
     double2 W2[KB][4][NB_PAD];         // w~ of the previous block
     double Rb[JP_MAX];                 // frame change factors applied to the state at the block start
-    double2 T0[KB][JC_MAX];            // v~_i - g_i per term
-    double2 G[KB][JC_MAX];             // g_i per term
+    double2 T0[KB][JC_MAX];            // v~_i - g_i per term (g_i stale by the previous block's update)
+    double2 TP[KB][JC_MAX];            // t~ of the previous block per term, in the current block's frame
     double2 F[JC_MAX];                 // forward-substitution state, frame of the current block
-    double dot[16];
-    int kk, kprev, flag, pad;          // block descriptor, written by chain thread 0
+    double dot[32];
+    int kk, flag, pad0, pad1;          // block descriptor, written by chain thread 0
 };
 static_assert(sizeof(FastSmem) % 16 == 0, "BlkSmem follows FastSmem in dynamic shared memory");
 static_assert(sizeof(FastSmem) + sizeof(BlkSmem) <= 227 * 1024, "shared memory");
@@ -149,53 +153,9 @@ __device__ __forceinline__ void blk_matvec(const double (&S)[TILE][TILE], const 
 }
 
 // ------------------------------------------------------------------------------------------
-// C1 / C2: data-parallel over the 352 non-producer threads, x = 0 .. 351
+// matrix loop: products of block B (stale by block B-1), then the rank-k update of block B-1
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void blk_c1(FastSmem &sm, BlkSmem &ex, const int x, const int n0, const int kk, const int Jc)
-{
-    for (int item = x; item < KB * JC_MAX; item += BLK_THREADS) {
-        const int i = item / JC_MAX, term = item - i * JC_MAX;
-        if (i >= kk || term >= Jc) continue;
-        const double2 *Pp = (i < 2) ? reinterpret_cast<const double2 *>(&sm.P[i][0][0])
-                                    : reinterpret_cast<const double2 *>(&ex.P23[i - 2][0][0]);
-        const int tixA = pchunk(term, 0), tixB = pchunk(term, 1);
-        double gc = 0.0, gs = 0.0;
-#pragma unroll
-        for (int s = 0; s < NSLOT; ++s) {
-            const double2 v = Pp[s * (JP_MAX / 2) + ((s & 1) ? tixB : tixA)];
-            gc += v.x; gs += v.y;
-        }
-        const double2 vn = sm.RV[(n0 + i) & (RR - 1)][term];
-        ex.G[i][term] = make_double2(gc, gs);
-        ex.T0[i][term] = make_double2(vn.x - gc, vn.y - gs);
-    }
-}
-
-__device__ __forceinline__ void blk_c2(FastSmem &sm, BlkSmem &ex, const int x, const int n0, const int kk, const int Jc)
-{
-    // one dot product per half-warp: 14 of the 22 half-warps, all in flight at once
-    const int id = x >> 4, hl = x & 15;
-    int i = 0, m = 0, kind = 0;
-    if (id < 4) { kind = 0; i = id; }
-    else if (id < 8) { kind = 1; i = id - 4; }
-    else if (id < 14) { kind = 2; const int r = id - 8; i = (r < 1) ? 1 : (r < 3) ? 2 : 3; m = r - i * (i - 1) / 2; }
-    const bool on = id < 14 && i < kk;
-    double acc = 0.0;
-    if (on) {
-        const double2 *U = sm.RU[(n0 + i) & (RR - 1)];
-        const double2 *Y = (kind == 0) ? ex.G[i] : (kind == 1) ? ex.F : ex.T0[m];
-        for (int t = hl; t < Jc; t += 16) {
-            const double2 u = U[t], y = Y[t];
-            acc = fma(u.x, y.x, acc);
-            acc = fma(u.y, y.y, acc);
-        }
-    }
-#pragma unroll
-    for (int off = 8; off >= 1; off >>= 1) acc += shfl_xor_d(acc, off);
-    if (on && hl == 0) ex.dot[id] = acc;
-}
-
-__device__ __forceinline__ void blk_matrix_loop(FastSmem &sm, BlkSmem &ex, const int mt, const int nsb, const int Jc)
+__device__ __forceinline__ void blk_matrix_loop(FastSmem &sm, BlkSmem &ex, const int mt, const int nsb)
 {
     const MatConst mc = make_mat_const(sm, make_tile_map(mt, nsb));
     const int bi = geom_bi(mc.geom), bj = geom_bj(mc.geom);
@@ -206,27 +166,11 @@ __device__ __forceinline__ void blk_matrix_loop(FastSmem &sm, BlkSmem &ex, const
     for (int i = 0; i < TILE; ++i)
 #pragma unroll
         for (int j = 0; j < TILE; ++j) S[i][j] = 0.0;
-    int n0 = 0;
-#ifdef GF_BLK_TIMING
-    long long tm[6] = {0, 0, 0, 0, 0, 0};
-    long long tc = clock64();
-#define GF_TICK(k) { const long long now_ = clock64(); tm[k] += now_ - tc; tc = now_; }
-#else
-#define GF_TICK(k)
-#endif
+    int kprev = 0;
     for (;;) {
-        bar_sync(BAR_D, BLK_THREADS);
-        GF_TICK(0)
-        const int kk = ex.kk, kprev = ex.kprev, flag = ex.flag;
+        bar_sync(BAR_S3, BLK_THREADS);          // rows, frame factors and descriptor of this block
+        const int kk = ex.kk, flag = ex.flag;
         if (kk == 0) break;
-        if (kprev > 0) blk_update<0>(S, tb, wc);
-        if (kprev > 1) blk_update<1>(S, tb, wc);
-        if (kprev > 2) blk_update<2>(S, tb, wc);
-        if (kprev > 3) blk_update<3>(S, tb, wc);
-#ifdef GF_BLK_TIMING
-        { double chk = S[0][0] + S[7][7] + S[3][4]; asm volatile("" :: "d"(chk)); }
-        GF_TICK(5)
-#endif
         if (flag) {
 #pragma unroll
             for (int i = 0; i < TILE; ++i) {
@@ -243,22 +187,15 @@ __device__ __forceinline__ void blk_matrix_loop(FastSmem &sm, BlkSmem &ex, const
             if (kk > 2) blk_matvec<2>(S, mc, ub, uc, ur, uj, kk > 3);
             if (kk > 3) blk_matvec<3>(S, mc, ub, uc, ur, uj, false);
         }
-        GF_TICK(1)
-        bar_sync(BAR_A, BLK_THREADS);
-        GF_TICK(2)
-        blk_c1(sm, ex, mt, n0, kk, Jc);
-        bar_sync(BAR_B, BLK_THREADS);
-        GF_TICK(3)
-        blk_c2(sm, ex, mt, n0, kk, Jc);
-        bar_sync(BAR_C, BLK_THREADS);
-        GF_TICK(4)
-        n0 += kk;
+        bar_arrive(BAR_S1, BLK_THREADS);        // partial products of this block are in P
+        bar_sync(BAR_S2, BLK_THREADS);          // t~, w~ of the previous block, in this block's frame
+        if (kprev > 0) blk_update<0>(S, tb, wc);
+        if (kprev > 1) blk_update<1>(S, tb, wc);
+        if (kprev > 2) blk_update<2>(S, tb, wc);
+        if (kprev > 3) blk_update<3>(S, tb, wc);
+        bar_arrive(BAR_S4, BLK_THREADS);        // T2 / W2 may be overwritten
+        kprev = kk;
     }
-#ifdef GF_BLK_TIMING
-    if (blockIdx.x == 0 && (mt & 31) == 0)
-        printf("matrix warp %d, cycles per row: wait D %.0f | updates %.0f | products %.0f | wait A %.0f | C1 + B %.0f | C2 + C %.0f\n", mt >> 5,
-               (double)tm[0] / n0, (double)tm[5] / n0, (double)tm[1] / n0, (double)tm[2] / n0, (double)tm[3] / n0, (double)tm[4] / n0);
-#endif
 }
 
 // rows of the block that starts at n1: up to KB rows of one ring half, none but the first changes the frame
@@ -269,60 +206,177 @@ __device__ __forceinline__ int blk_rows(const FastSmem &sm, const int n1, const 
     return k;
 }
 
+// dot products of a block: 4 q_i, 4 f_i, 6 M0_im (m < i), 16 cross c'_im (previous block's t~_m)
+constexpr int N_DOTS = 30;
+__device__ __forceinline__ int dot_id_x(int i, int m) { return 14 + 4 * i + m; }
+
+// ------------------------------------------------------------------------------------------
+// chain loop (three warps): everything of block B while the matrix warps work on block B + 1
+// ------------------------------------------------------------------------------------------
 template <int MODE>
 __device__ __forceinline__ void blk_chain_loop(FastSmem &sm, BlkSmem &ex, const ScanArgs &A, const int ht,
                                                const int b, const int N, const int Jc)
 {
-    const int x = MAT_THREADS + ht;
     const int term = ht;
     const bool act = term < Jc;
     const int tq = term & 3, tb = term >> 2;          // element pair / block of this term's two columns
+    const int hw16 = ht >> 4, hl = ht & 15;           // half-warp and lane in it (dot products)
     const long long n0g = A.n_off[b];
     const int nh = (int)ring_halves(N);
 
     bar_sync(BAR_FULL + 0, N_RING);                   // ring half 0: rows 0..7
-    int n0 = 0;
-    {
-        const int kk0 = blk_rows(sm, 0, N);
-        if (act) {
+    int n0 = 0, kk = blk_rows(sm, 0, N), kp = 0;
+    if (act) {
 #pragma unroll
-            for (int i = 0; i < KB; ++i)
-                if (i < kk0) ex.U2[i][tq][tb] = sm.RU[i][term];
-        }
-        if (ht == 0) { ex.kk = kk0; ex.kprev = 0; ex.flag = 0; }
+        for (int i = 0; i < KB; ++i)
+            if (i < kk) ex.U2[i][tq][tb] = sm.RU[i][term];
     }
+    if (ht == 0) { ex.kk = kk; ex.flag = 0; }
+    bar_sync(BAR_CH, CH_THREADS);
+    bar_arrive(BAR_S3, BLK_THREADS);                  // block 0 can start
+    bar_arrive(BAR_S2, BLK_THREADS);                  // "the update before block 0": nothing
+    double rdp[KB] = {0.0, 0.0, 0.0, 0.0};            // 1 / d of the previous block
     double logsum = 0.0, prod = 1.0, quad = 0.0;
     int esum = 0;
     int32_t fail = 0;
+    bool dead = false;
+#ifdef GF_BLK_TIMING
+    long long tm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tc = clock64();
+#define GF_TICK(k) { const long long now_ = clock64(); tm[k] += now_ - tc; tc = now_; }
+#else
+#define GF_TICK(k)
+#endif
 
     for (;;) {
-        bar_sync(BAR_D, BLK_THREADS);
-        const int kk = ex.kk;
-        if (kk == 0) break;
-        bar_sync(BAR_A, BLK_THREADS);
-        blk_c1(sm, ex, x, n0, kk, Jc);
-        bar_sync(BAR_B, BLK_THREADS);
-        blk_c2(sm, ex, x, n0, kk, Jc);
-        bar_sync(BAR_C, BLK_THREADS);
+        bar_sync(BAR_S1, BLK_THREADS);                // partial products of block [n0, n0 + kk)
+        GF_TICK(0)
+        const int n1 = n0 + kk;
+        if (dead) {
+            // the block after a non-positive pivot: only the hand-shakes, and stop the matrix warps
+            if (ht == 0) ex.kk = 0;
+            bar_sync(BAR_CH, CH_THREADS);
+            bar_arrive(BAR_S3, BLK_THREADS);
+            bar_sync(BAR_S4, BLK_THREADS);
+            break;
+        }
+        // ---- C1: g-sums, T0_i = v~_i - g_i ----------------------------------------------------
+        for (int item = ht; item < KB * JC_MAX; item += CH_THREADS) {
+            const int i = item / JC_MAX, tm = item - i * JC_MAX;
+            if (i >= kk || tm >= Jc) continue;
+            const double2 *Pp = (i < 2) ? reinterpret_cast<const double2 *>(&sm.P[i][0][0])
+                                        : reinterpret_cast<const double2 *>(&ex.P23[i - 2][0][0]);
+            const int tixA = pchunk(tm, 0), tixB = pchunk(tm, 1);
+            double2 v[NSLOT];
+#pragma unroll
+            for (int s = 0; s < NSLOT; ++s) v[s] = Pp[s * (JP_MAX / 2) + ((s & 1) ? tixB : tixA)];
+            const double gc = (((v[0].x + v[1].x) + (v[2].x + v[3].x)) + ((v[4].x + v[5].x) + (v[6].x + v[7].x))) +
+                              ((v[8].x + v[9].x) + (v[10].x + v[11].x));
+            const double gs = (((v[0].y + v[1].y) + (v[2].y + v[3].y)) + ((v[4].y + v[5].y) + (v[6].y + v[7].y))) +
+                              ((v[8].y + v[9].y) + (v[10].y + v[11].y));
+            const double2 vn = sm.RV[(n0 + i) & (RR - 1)][tm];
+            ex.T0[i][tm] = make_double2(vn.x - gc, vn.y - gs);
+        }
+        GF_TICK(1)
+        // ---- ring: the rows of this block are touched; the next block's rows must be there -------
+        for (int n = n0; n < n1; ++n)
+            if (((n + 2) & (HALF - 1)) == 0 && (n + 2) / HALF < nh)
+                bar_sync(BAR_FULL + (((n + 2) / HALF) & 1), N_RING);
+        // ---- next block: rows, frame change, descriptor (the matrix warps start it right away) ---
+        const bool more = n1 < N;
+        int kk1 = 0, flag1 = 0;
+        if (more) { kk1 = blk_rows(sm, n1, N); flag1 = sm.Rflag[n1 & (RR - 1)]; }
+        const double r1 = (act && more && flag1) ? sm.Rr[n1 & (RR - 1)][term] : 1.0;
+        if (act) {
+#pragma unroll
+            for (int i = 0; i < KB; ++i)
+                if (i < kk1) ex.U2[i][tq][tb] = sm.RU[(n1 + i) & (RR - 1)][term];
+            ex.Rb[2 * term] = r1; ex.Rb[2 * term + 1] = r1;
+        }
+        if (ht == 0) { ex.kk = kk1; ex.flag = flag1; }
+        bar_sync(BAR_CH, CH_THREADS);                 // T0 complete, P consumed, next rows written
+        bar_arrive(BAR_S3, BLK_THREADS);
+        GF_TICK(2)
 
-        // ---- C3: scalar recursion (every lane) ---------------------------------------------
-        double e[KB][KB], cc[KB][KB], rd[KB], dd[KB], zz[KB], xx[KB];
+        // ---- C2: one batch of dot products.  All dot products of a row share the operand u~_i: a
+        // half-warp walks the terms once and keeps up to seven independent accumulators.
+        //   half-warp 0: row 0 (q, f, cross 0..3)      1: row 1 (q, f, M10, cross)
+        //             2: row 2 (q, f, M20, M21)         3: row 2 (cross)
+        //             4: row 3 (q, f, M30, M31, M32)    5: row 3 (cross)
+        {
+            const int row = (hw16 < 2) ? hw16 : ((hw16 < 4) ? 2 : 3);
+            const bool doQF = (hw16 != 3) && (hw16 != 5);
+            const bool doX = (hw16 < 2) || hw16 == 3 || hw16 == 5;
+            double aq0 = 0.0, aq1 = 0.0, af0 = 0.0, af1 = 0.0, am[3] = {0.0, 0.0, 0.0}, ax[KB] = {0.0, 0.0, 0.0, 0.0};
+            if (row < kk) {
+                const int slot = (n0 + row) & (RR - 1);
+                const double2 *U = sm.RU[slot];
+                for (int t = hl; t < Jc; t += 16) {
+                    const double2 u = U[t];
+                    if (doQF) {
+                        const double2 vv = sm.RV[slot][t], t0 = ex.T0[row][t], Ft = ex.F[t];
+                        aq0 = fma(u.x, vv.x - t0.x, aq0); aq1 = fma(u.y, vv.y - t0.y, aq1);
+                        af0 = fma(u.x, Ft.x, af0); af1 = fma(u.y, Ft.y, af1);
+#pragma unroll
+                        for (int m = 0; m < 3; ++m)
+                            if (m < row) { const double2 y = ex.T0[m][t]; am[m] = fma(u.x, y.x, fma(u.y, y.y, am[m])); }
+                    }
+                    if (doX) {
+#pragma unroll
+                        for (int m = 0; m < KB; ++m)
+                            if (m < kp) { const double2 y = ex.TP[m][t]; ax[m] = fma(u.x, y.x, fma(u.y, y.y, ax[m])); }
+                    }
+                }
+            }
+            double aq = aq0 + aq1, af = af0 + af1;
+#pragma unroll
+            for (int off = 8; off >= 1; off >>= 1) {
+                aq += shfl_xor_d(aq, off); af += shfl_xor_d(af, off);
+#pragma unroll
+                for (int m = 0; m < 3; ++m) am[m] += shfl_xor_d(am[m], off);
+#pragma unroll
+                for (int m = 0; m < KB; ++m) ax[m] += shfl_xor_d(ax[m], off);
+            }
+            if (hl == 0 && row < kk) {
+                if (doQF) {
+                    ex.dot[dot_id_q(row)] = aq; ex.dot[dot_id_f(row)] = af;
+#pragma unroll
+                    for (int m = 0; m < 3; ++m) if (m < row) ex.dot[dot_id_m(row, m)] = am[m];
+                }
+                if (doX) {
+#pragma unroll
+                    for (int m = 0; m < KB; ++m) ex.dot[dot_id_x(row, m)] = ax[m];
+                }
+            }
+        }
+        bar_sync(BAR_CH, CH_THREADS);
+        GF_TICK(3)
+
+        // ---- C3: scalar recursion over the window (previous block + this one), every lane --------
+        double cp[KB][KB], ep[KB][KB], e[KB][KB], cc[KB][KB], rd[KB], dd[KB], zz[KB], xx[KB];
         int bad = -1;
 #pragma unroll
         for (int i = 0; i < KB; ++i) {
             rd[i] = 0.0; dd[i] = 1.0; zz[i] = 0.0; xx[i] = 0.0;
 #pragma unroll
-            for (int m = 0; m < KB; ++m) { e[i][m] = 0.0; cc[i][m] = 0.0; }
+            for (int m = 0; m < KB; ++m) { e[i][m] = 0.0; cc[i][m] = 0.0; cp[i][m] = 0.0; ep[i][m] = 0.0; }
             if (i < kk) {
                 const int slot = (n0 + i) & (RR - 1);
 #pragma unroll
+                for (int m = 0; m < KB; ++m)
+                    if (m < kp) { cp[i][m] = ex.dot[dot_id_x(i, m)]; ep[i][m] = cp[i][m] * rdp[m]; }
+#pragma unroll
                 for (int m = 0; m < i; ++m) {
                     double c = ex.dot[dot_id_m(i, m)];
+#pragma unroll
+                    for (int l = 0; l < KB; ++l) c = fma(-ep[m][l], cp[i][l], c);
 #pragma unroll
                     for (int l = 0; l < m; ++l) c = fma(-e[m][l], cc[i][l], c);
                     cc[i][m] = c;
                 }
                 double acc = ex.dot[dot_id_q(i)];
+#pragma unroll
+                for (int m = 0; m < KB; ++m) acc = fma(ep[i][m], cp[i][m], acc);
 #pragma unroll
                 for (int m = 0; m < i; ++m) {
                     e[i][m] = cc[i][m] * rd[m];
@@ -331,8 +385,7 @@ __device__ __forceinline__ void blk_chain_loop(FastSmem &sm, BlkSmem &ex, const 
                 dd[i] = sm.Ra[slot] - acc;
                 if (!(dd[i] > 0.0) && bad < 0) bad = i;
                 rd[i] = fast_rcp(dd[i]);
-                const double fi = ex.dot[dot_id_f(i)];
-                double corr = fi;
+                double corr = ex.dot[dot_id_f(i)];
 #pragma unroll
                 for (int m = 0; m < i; ++m) corr = fma(e[i][m], zz[m], corr);
                 if (MODE == MODE_LOGLIKE) {
@@ -344,25 +397,26 @@ __device__ __forceinline__ void blk_chain_loop(FastSmem &sm, BlkSmem &ex, const 
             }
         }
         const int good = (bad < 0) ? kk : bad;        // rows of this block with a positive pivot
+#ifdef GF_BLK_TIMING
+        { double chk = rd[0] + rd[3] + zz[3]; asm volatile("" :: "d"(chk)); }
+#endif
+        GF_TICK(4)
 
-        // ---- ring: rows n0 .. n0 + kk - 1 are touched, the next block's rows must be there ------
-        for (int n = n0; n < n0 + kk; ++n)
-            if (((n + 2) & (HALF - 1)) == 0 && (n + 2) / HALF < nh)
-                bar_sync(BAR_FULL + (((n + 2) / HALF) & 1), N_RING);
-
-        // ---- C4: vectors, next block ----------------------------------------------------------
-        const int n1 = n0 + kk;
-        const bool more = (bad < 0) && n1 < N;
-        int kk1 = 0, flag1 = 0;
-        if (more) { kk1 = blk_rows(sm, n1, N); flag1 = sm.Rflag[n1 & (RR - 1)]; }
+        // ---- C4: vectors ---------------------------------------------------------------------------
+        double2 tt[KB], ww[KB];
+#pragma unroll
+        for (int i = 0; i < KB; ++i) { tt[i] = make_double2(0.0, 0.0); ww[i] = make_double2(0.0, 0.0); }
         if (act) {
-            double2 tt[KB], ww[KB];
+            double2 tp[KB];
+#pragma unroll
+            for (int m = 0; m < KB; ++m) tp[m] = (m < kp) ? ex.TP[m][term] : make_double2(0.0, 0.0);
             double2 F = ex.F[term];
 #pragma unroll
             for (int i = 0; i < KB; ++i) {
-                tt[i] = make_double2(0.0, 0.0); ww[i] = make_double2(0.0, 0.0);
                 if (i < kk) {
                     double2 T = ex.T0[i][term];
+#pragma unroll
+                    for (int m = 0; m < KB; ++m) { T.x = fma(-ep[i][m], tp[m].x, T.x); T.y = fma(-ep[i][m], tp[m].y, T.y); }
 #pragma unroll
                     for (int m = 0; m < i; ++m) { T.x = fma(-e[i][m], tt[m].x, T.x); T.y = fma(-e[i][m], tt[m].y, T.y); }
                     tt[i] = T;
@@ -371,14 +425,6 @@ __device__ __forceinline__ void blk_chain_loop(FastSmem &sm, BlkSmem &ex, const 
                     F.y = fma(ww[i].y, zz[i], F.y);
                 }
             }
-            const double r1 = (more && flag1) ? sm.Rr[n1 & (RR - 1)][term] : 1.0;
-#pragma unroll
-            for (int i = 0; i < KB; ++i) {
-                ex.T2[i][tq][tb] = tt[i];
-                ex.W2[i][tq][tb] = ww[i];
-                if (i < kk1) ex.U2[i][tq][tb] = sm.RU[(n1 + i) & (RR - 1)][term];
-            }
-            ex.Rb[2 * term] = r1; ex.Rb[2 * term + 1] = r1;
             ex.F[term] = make_double2(F.x * r1, F.y * r1);
         }
         if (ht == 0) {
@@ -389,18 +435,44 @@ __device__ __forceinline__ void blk_chain_loop(FastSmem &sm, BlkSmem &ex, const 
                     if (MODE == MODE_LOGLIKE) quad = fma(zz[i] * zz[i], rd[i], quad);
                     else A.out_x[n0g + n0 + i] = xx[i];
                 }
-            logsum += log(prod); prod = 1.0;
-            ex.kk = more ? kk1 : 0; ex.kprev = kk; ex.flag = flag1;
-            if (bad >= 0) sm.stop = n0 + bad;       // the producer keeps only the hand-shake going
+            if ((n1 & 31) < KB || !more) { logsum += log(prod); prod = 1.0; }
+            if (bad >= 0) sm.stop = n0 + bad;         // the producer keeps only the hand-shake going
         }
-        if (bad >= 0) fail = n0 + bad + 1;
+        if (bad >= 0) { fail = n0 + bad + 1; dead = true; }
+
+        GF_TICK(5)
+        bar_sync(BAR_S4, BLK_THREADS);                // the update of the previous block is applied
+        GF_TICK(6)
+        if (act) {
+#pragma unroll
+            for (int i = 0; i < KB; ++i) {
+                const double2 t1 = make_double2(tt[i].x * r1, tt[i].y * r1);
+                ex.T2[i][tq][tb] = t1;
+                ex.W2[i][tq][tb] = make_double2(ww[i].x * r1, ww[i].y * r1);
+                ex.TP[i][term] = t1;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < KB; ++i) rdp[i] = rd[i];
+        if (kk1 > 0) {
+            bar_sync(BAR_CH, CH_THREADS);             // all of T2 / W2 written
+            bar_arrive(BAR_S2, BLK_THREADS);
+        }
         // ring: the rows of this block are dead
-        for (int n = n0; n < n0 + kk; ++n)
+        for (int n = n0; n < n1; ++n)
             if ((n & (HALF - 1)) == HALF - 1 && n / HALF + 2 < nh)
                 bar_arrive(BAR_EMPTY + ((n / HALF) & 1), N_RING);
-        n0 = n1;
+        kp = kk; n0 = n1; kk = kk1;
+        GF_TICK(7)
+        if (kk == 0) break;
     }
-    // not positive definite: keep the ring hand-shake with the producer going until the natural end
+#ifdef GF_BLK_TIMING
+    if (blockIdx.x == 0 && (ht & 31) == 0)
+        printf("chain warp %d, cycles per row: wait S1 %.0f | C1 %.0f | ring + next block + S3 %.0f | C2 %.0f | C3 %.0f | C4 %.0f | wait S4 %.0f | stores + S2 + ring %.0f\n",
+               ht >> 5, (double)tm[0] / N, (double)tm[1] / N, (double)tm[2] / N, (double)tm[3] / N, (double)tm[4] / N,
+               (double)tm[5] / N, (double)tm[6] / N, (double)tm[7] / N);
+#endif
+    // after a non-positive pivot: keep the ring hand-shake with the producer going until the natural end
     for (int n = n0; n < N; ++n) {
         if (((n + 2) & (HALF - 1)) == 0 && (n + 2) / HALF < nh)
             bar_sync(BAR_FULL + (((n + 2) / HALF) & 1), N_RING);
@@ -408,6 +480,7 @@ __device__ __forceinline__ void blk_chain_loop(FastSmem &sm, BlkSmem &ex, const 
             bar_arrive(BAR_EMPTY + ((n / HALF) & 1), N_RING);
     }
     if (ht == 0) {
+        if (prod != 1.0) logsum += log(prod);
         A.logdet[b] = logdet_total(logsum, 1.0, esum);
         if (MODE == MODE_LOGLIKE && A.quad) A.quad[b] = quad;
         A.status[b] = fail;
@@ -434,8 +507,8 @@ __global__ void __launch_bounds__(FT_THREADS, 1) scan_blk_kernel(ScanArgs A)
         while (next_sequence(sm, A, tid, q)) {
             if (q.N > 0) {
                 reset(tid);
-                bar_sync(BAR_A, BLK_THREADS);
-                blk_matrix_loop(sm, ex, tid, q.nsb, q.Jc);
+                bar_sync(BAR_S1, BLK_THREADS);
+                blk_matrix_loop(sm, ex, tid, q.nsb);
             }
         }
     } else {
@@ -446,7 +519,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) scan_blk_kernel(ScanArgs A)
             while (next_sequence(sm, A, tid, q)) {
                 if (q.N > 0) {
                     reset(tid);
-                    bar_sync(BAR_A, BLK_THREADS);
+                    bar_sync(BAR_S1, BLK_THREADS);
                     blk_chain_loop<MODE>(sm, ex, A, ht, q.b, q.N, q.Jc);
                 } else if (ht == 0) {
                     A.logdet[q.b] = 0.0;
