@@ -298,54 +298,80 @@ __device__ __forceinline__ void blk_chain_loop(FastSmem &sm, BlkSmem &ex, const 
         bar_arrive(BAR_S3, BLK_THREADS);
         GF_TICK(2)
 
-        // ---- C2: one batch of dot products.  All dot products of a row share the operand u~_i: a
-        // half-warp walks the terms once and keeps up to seven independent accumulators.
-        //   half-warp 0: row 0 (q, f, cross 0..3)      1: row 1 (q, f, M10, cross)
-        //             2: row 2 (q, f, M20, M21)         3: row 2 (cross)
-        //             4: row 3 (q, f, M30, M31, M32)    5: row 3 (cross)
+        // ---- C2: one batch of dot products.  All dot products of a row share the operand u~_i; a WARP
+        // walks the terms once (three per lane) with one accumulator per dot product and reduces all of
+        // them in one transposing butterfly (16 shuffles for 16 values instead of 5 per value).
+        //   warp 0: rows 0, 1 (13 values)   warp 1: row 2 (8)   warp 2: row 3 (9)
         {
-            const int row = (hw16 < 2) ? hw16 : ((hw16 < 4) ? 2 : 3);
-            const bool doQF = (hw16 != 3) && (hw16 != 5);
-            const bool doX = (hw16 < 2) || hw16 == 3 || hw16 == 5;
-            double aq0 = 0.0, aq1 = 0.0, af0 = 0.0, af1 = 0.0, am[3] = {0.0, 0.0, 0.0}, ax[KB] = {0.0, 0.0, 0.0, 0.0};
-            if (row < kk) {
+            double v[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) v[k] = 0.0;
+            const int cw = ht >> 5, lane = ht & 31;
+            // accumulates (q, f, M_row,0.., cross 0..3) of `row` into v[base ...]
+            auto row_dots = [&](const int row, const int base, const int t) {
                 const int slot = (n0 + row) & (RR - 1);
-                const double2 *U = sm.RU[slot];
-                for (int t = hl; t < Jc; t += 16) {
-                    const double2 u = U[t];
-                    if (doQF) {
-                        const double2 vv = sm.RV[slot][t], t0 = ex.T0[row][t], Ft = ex.F[t];
-                        aq0 = fma(u.x, vv.x - t0.x, aq0); aq1 = fma(u.y, vv.y - t0.y, aq1);
-                        af0 = fma(u.x, Ft.x, af0); af1 = fma(u.y, Ft.y, af1);
+                const double2 u = sm.RU[slot][t], vv = sm.RV[slot][t], t0 = ex.T0[row][t], Ft = ex.F[t];
+                v[base] = fma(u.x, vv.x - t0.x, fma(u.y, vv.y - t0.y, v[base]));
+                v[base + 1] = fma(u.x, Ft.x, fma(u.y, Ft.y, v[base + 1]));
 #pragma unroll
-                        for (int m = 0; m < 3; ++m)
-                            if (m < row) { const double2 y = ex.T0[m][t]; am[m] = fma(u.x, y.x, fma(u.y, y.y, am[m])); }
-                    }
-                    if (doX) {
+                for (int m = 0; m < 3; ++m)
+                    if (m < row) { const double2 y = ex.T0[m][t]; v[base + 2 + m] = fma(u.x, y.x, fma(u.y, y.y, v[base + 2 + m])); }
 #pragma unroll
-                        for (int m = 0; m < KB; ++m)
-                            if (m < kp) { const double2 y = ex.TP[m][t]; ax[m] = fma(u.x, y.x, fma(u.y, y.y, ax[m])); }
-                    }
+                for (int m = 0; m < KB; ++m)
+                    if (m < kp) { const double2 y = ex.TP[m][t]; v[base + 2 + row + m] = fma(u.x, y.x, fma(u.y, y.y, v[base + 2 + row + m])); }
+            };
+            for (int t = lane; t < Jc; t += 32) {
+                if (cw == 0) { row_dots(0, 0, t); if (kk > 1) row_dots(1, 6, t); }
+                else if (cw == 1) { if (kk > 2) row_dots(2, 0, t); }
+                else { if (kk > 3) row_dots(3, 0, t); }
+            }
+            // transposing butterfly: after the stage with offset o a lane keeps the values whose index
+            // has the same bit as its lane bit; lane (b4 b3 b2 b1 *) ends with value b4 + 2 b3 + 4 b2 + 8 b1
+            double w8[8], w4[4], w2[2], w1;
+            {
+                const bool hi = (lane & 16) != 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const double keep = hi ? v[2 * k + 1] : v[2 * k], send = hi ? v[2 * k] : v[2 * k + 1];
+                    w8[k] = keep + shfl_xor_d(send, 16);
                 }
             }
-            double aq = aq0 + aq1, af = af0 + af1;
+            {
+                const bool hi = (lane & 8) != 0;
 #pragma unroll
-            for (int off = 8; off >= 1; off >>= 1) {
-                aq += shfl_xor_d(aq, off); af += shfl_xor_d(af, off);
-#pragma unroll
-                for (int m = 0; m < 3; ++m) am[m] += shfl_xor_d(am[m], off);
-#pragma unroll
-                for (int m = 0; m < KB; ++m) ax[m] += shfl_xor_d(ax[m], off);
-            }
-            if (hl == 0 && row < kk) {
-                if (doQF) {
-                    ex.dot[dot_id_q(row)] = aq; ex.dot[dot_id_f(row)] = af;
-#pragma unroll
-                    for (int m = 0; m < 3; ++m) if (m < row) ex.dot[dot_id_m(row, m)] = am[m];
+                for (int k = 0; k < 4; ++k) {
+                    const double keep = hi ? w8[2 * k + 1] : w8[2 * k], send = hi ? w8[2 * k] : w8[2 * k + 1];
+                    w4[k] = keep + shfl_xor_d(send, 8);
                 }
-                if (doX) {
+            }
+            {
+                const bool hi = (lane & 4) != 0;
 #pragma unroll
-                    for (int m = 0; m < KB; ++m) ex.dot[dot_id_x(row, m)] = ax[m];
+                for (int k = 0; k < 2; ++k) {
+                    const double keep = hi ? w4[2 * k + 1] : w4[2 * k], send = hi ? w4[2 * k] : w4[2 * k + 1];
+                    w2[k] = keep + shfl_xor_d(send, 4);
+                }
+            }
+            {
+                const bool hi = (lane & 2) != 0;
+                const double keep = hi ? w2[1] : w2[0], send = hi ? w2[0] : w2[1];
+                w1 = keep + shfl_xor_d(send, 2);
+            }
+            w1 += shfl_xor_d(w1, 1);
+            if ((lane & 1) == 0) {
+                const int idx = ((lane >> 4) & 1) + 2 * ((lane >> 3) & 1) + 4 * ((lane >> 2) & 1) + 8 * ((lane >> 1) & 1);
+                // value index -> (row, which dot)
+                int row, j;
+                if (cw == 0) { row = (idx < 6) ? 0 : 1; j = (idx < 6) ? idx : idx - 6; }
+                else { row = cw + 1; j = idx; }
+                const int nv = 2 + row + KB;                 // q, f, M_row,0 .. M_row,row-1, cross 0..3
+                if (row < kk && j < nv && (cw != 0 || idx < 13)) {
+                    int id;
+                    if (j == 0) id = dot_id_q(row);
+                    else if (j == 1) id = dot_id_f(row);
+                    else if (j < 2 + row) id = dot_id_m(row, j - 2);
+                    else id = dot_id_x(row, j - 2 - row);
+                    ex.dot[id] = w1;
                 }
             }
         }
